@@ -1,0 +1,143 @@
+// Op-level C-ABI entry points (parity tests drive single kernels through these) and small utilities.
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/b200ad.h"
+#include "conv_tc.cuh"
+#include "kernels.cuh"
+
+namespace b200ad {
+int set_err(const char* fmt, ...);
+}
+using namespace b200ad;
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) return set_err("%s: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct ConvScratch {
+  size_t x, par, res, out, wpack, stats, total;
+};
+static ConvScratch conv_scratch_layout(int N, int cin, int cout, int H, int W, int K, int stride) {
+  ConvScratch s{};
+  const Geom gi = make_geom(N, H, W);
+  const int Ho = H / stride, Wo = W / stride;
+  const Geom go = make_geom(N, Ho, Wo);
+  size_t off = 0;
+  s.x = off; off = al(off + (size_t)N * (cin / 8) * gi.PL * 16);
+  s.par = off; if (stride == 2) off = al(off + (size_t)4 * N * (cin / 8) * go.PL * 16);
+  s.res = off; off = al(off + (size_t)N * (cout / 8) * go.PL * 16);
+  s.out = off; off = al(off + (size_t)N * (cout / 8) * go.PL * 16);
+  s.wpack = off; off = al(off + (size_t)(cout / 128) * (cin / 16) * K * K * CONV_B_TAP);
+  s.stats = off; off = al(off + (size_t)N * (cout / 4) * 2 * 4);
+  s.total = off;
+  return s;
+}
+
+extern "C" size_t b200ad_conv2d_scratch_bytes(int N, int cin, int cout, int H, int W, int K, int stride) {
+  return conv_scratch_layout(N, cin, cout, H, W, K, stride).total;
+}
+
+extern "C" int b200ad_conv2d(const float* x, const float* w, const float* bias, const float* temb, const float* residual,
+                             float* y, float* stats_out, int N, int cin, int cout, int H, int W, int K, int stride,
+                             void* scratch, size_t scratch_bytes, void* stream) {
+  if (cin % 16 || cout % 128) return set_err("conv2d: cin %% 16 and cout %% 128 must be 0");
+  if (!((K == 3 || K == 1) && (stride == 1 || (stride == 2 && K == 3)))) return set_err("conv2d: unsupported K/stride");
+  if (stride == 2 && (H % 2 || W % 2)) return set_err("conv2d: stride 2 needs even H, W");
+  const ConvScratch L = conv_scratch_layout(N, cin, cout, H, W, K, stride);
+  if (scratch_bytes < L.total) return set_err("conv2d: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* sb = (uint8_t*)scratch;
+  CK(cudaMemsetAsync(sb, 0, L.total, st));
+  const int Ho = H / stride, Wo = W / stride;
+  const Geom go = make_geom(N, Ho, Wo);
+  __nv_bfloat16* xp = (__nv_bfloat16*)(sb + L.x);
+  __nv_bfloat16* par = (__nv_bfloat16*)(sb + L.par);
+  __nv_bfloat16* rp = (__nv_bfloat16*)(sb + L.res);
+  __nv_bfloat16* op = (__nv_bfloat16*)(sb + L.out);
+  __nv_bfloat16* wp = (__nv_bfloat16*)(sb + L.wpack);
+  float* stp = (float*)(sb + L.stats);
+  CK(launch_nchw_to_pf8(x, xp, N, cin, H, W, st));
+  if (residual) CK(launch_nchw_to_pf8(residual, rp, N, cout, Ho, Wo, st));
+
+  ConvParams p{};
+  p.N = N; p.H = Ho; p.W = Wo; p.Wp = go.Wp; p.lead = go.lead; p.PL = go.PL;
+  p.wide = (Wo % 128 == 0) ? 1 : 0;
+  p.groups_per_img = p.wide ? ((Ho + CONV_MAXG - 1) / CONV_MAXG) * (Wo / 128)
+                            : (Ho * go.Wp + CONV_MAXG * CONV_TM - 1) / (CONV_MAXG * CONV_TM);
+  p.cout = cout; p.ntiles_n = cout / 128;
+  p.total_work = N * p.groups_per_img * p.ntiles_n;
+  p.out = op; p.bias = bias; p.temb = temb; p.temb_stride = cout; p.res = residual ? rp : nullptr;
+  p.stats = stats_out ? stp : nullptr;
+  const long long img_stride = (long long)(cin / 8) * go.PL * 8;
+  if (stride == 1) {
+    PackTaps t{};
+    t.ntaps = K * K;
+    for (int k = 0; k < K * K; ++k) { t.kh[k] = k / K; t.kw[k] = k % K; }
+    CK(launch_pack_weights(w, cout, cin, K, K, 0, cin / 16, t, wp, st));
+    ConvSeg& s = p.seg[0];
+    s.src = xp; s.wpack = wp; s.img_stride = img_stride; s.ksteps = cin / 16; s.ntaps = K * K;
+    s.ht = s.hb = s.hl = s.hr = (K == 3) ? 1 : 0;
+    for (int k = 0; k < K * K; ++k) { s.dh[k] = (signed char)(k / K - K / 2); s.dw[k] = (signed char)(k % K - K / 2); }
+    p.nseg = 1;
+  } else {
+    CK(launch_parity_split(xp, par, N, cin, H, W, st));
+    const size_t tsz = (size_t)N * (cin / 8) * go.PL * 8;
+    size_t woff = 0;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        PackTaps t{};
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw)
+            if (((kh == 1) ? 0 : 1) == a && ((kw == 1) ? 0 : 1) == b) { t.kh[t.ntaps] = kh; t.kw[t.ntaps] = kw; ++t.ntaps; }
+        __nv_bfloat16* wseg = wp + woff / 2;
+        CK(launch_pack_weights(w, cout, cin, 3, 3, 0, cin / 16, t, wseg, st));
+        woff += (size_t)(cout / 128) * (cin / 16) * t.ntaps * CONV_B_TAP;
+        ConvSeg& s = p.seg[a * 2 + b];
+        s.src = par + (size_t)(a * 2 + b) * tsz; s.wpack = wseg; s.img_stride = img_stride; s.ksteps = cin / 16;
+        s.ntaps = t.ntaps;
+        s.ht = a; s.hb = 0; s.hl = b; s.hr = 0;
+        for (int k = 0; k < t.ntaps; ++k) { s.dh[k] = (t.kh[k] == 0) ? -1 : 0; s.dw[k] = (t.kw[k] == 0) ? -1 : 0; }
+      }
+    p.nseg = 4;
+  }
+  int dev = 0, sms = 148;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CK(launch_conv_tc(p, sms, st));
+  CK(launch_pf8_to_nchw(op, y, N, cout, Ho, Wo, st));
+  if (stats_out) CK(cudaMemcpyAsync(stats_out, stp, (size_t)N * (cout / 4) * 2 * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+extern "C" int b200ad_group_norm(const float* x, const float* gamma, const float* beta, float* y, int N, int C, int H,
+                                 int W, int groups, float eps, int silu, void* scratch, size_t scratch_bytes, void* stream) {
+  if (C % 32) return set_err("group_norm: C %% 32 != 0");
+  const Geom g = make_geom(N, H, W);
+  const size_t tb = al((size_t)N * (C / 8) * g.PL * 16);
+  const size_t need = 2 * tb + al((size_t)N * (C / 4) * 8);
+  if (scratch_bytes < need) return set_err("group_norm: scratch too small (%zu < %zu)", scratch_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* sb = (uint8_t*)scratch;
+  CK(cudaMemsetAsync(sb, 0, need, st));
+  __nv_bfloat16* xp = (__nv_bfloat16*)sb;
+  __nv_bfloat16* yp = (__nv_bfloat16*)(sb + tb);
+  float* stats = (float*)(sb + 2 * tb);
+  CK(launch_nchw_to_pf8(x, xp, N, C, H, W, st));
+  CK(launch_quad_stats(xp, stats, N, C, H, W, st));
+  GnApplyParams p{};
+  p.src[0] = xp; p.stats[0] = stats; p.C[0] = C; p.src[1] = nullptr; p.stats[1] = nullptr; p.C[1] = 0;
+  p.gamma = gamma; p.beta = beta; p.dst = yp; p.N = N; p.H = H; p.W = W; p.groups = groups; p.eps = eps; p.silu = silu;
+  CK(launch_gn_apply(p, st));
+  CK(launch_pf8_to_nchw(yp, y, N, C, H, W, st));
+  return 0;
+}
+
+extern "C" int b200ad_sample_to_u8(const float* x, uint8_t* img, size_t n, void* stream) {
+  CK(launch_sample_to_u8(x, img, n, (cudaStream_t)stream));
+  return 0;
+}

@@ -1,0 +1,466 @@
+// SIMT kernels of the U-Net path that are HBM-bound or degenerate for tensor cores:
+// weight packing, GroupNorm(+SiLU) apply, conv_in (Cin = 1), conv_norm_out + conv_out (Cout = 1) fused with
+// the DDPM/DDIM update, nearest-2x upsample, stride-2 parity split and layout conversion.
+// Reference semantics: diffusers UNet2DModel / DDPMScheduler.step / DDIMScheduler.step as called from
+// audiodiffusion/pipeline_audio_diffusion.py:163-179 (restated in oracle/unet_oracle.py, oracle/schedulers_oracle.py).
+#include "kernels.cuh"
+
+namespace b200ad {
+
+// ------------------------------------------------------------------------------------ weight packing
+__global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin_total, int KH, int KW, int cin_off,
+                                    int ksteps, PackTaps taps, __nv_bfloat16* __restrict__ dst, long long nvec) {
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= nvec) return;
+  const int r = (int)(id & 7);
+  const int n8 = (int)((id >> 3) & 15);
+  const int k8 = (int)((id >> 7) & 1);
+  long long rest = id >> 8;
+  const int tap = (int)(rest % taps.ntaps);
+  rest /= taps.ntaps;
+  const int ks = (int)(rest % ksteps);
+  const int ntile = (int)(rest / ksteps);
+  const int co = ntile * 128 + n8 * 8 + r;
+  const int ci0 = cin_off + ks * 16 + k8 * 8;
+  float v[8];
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    const float* wp = w + ((long long)co * cin_total + ci0 + kk) * KH * KW;
+    float a = 0.f;
+    if (taps.fold) {
+      const unsigned mask = taps.fold_mask[tap];
+      for (int t = 0; t < KH * KW; ++t)
+        if (mask & (1u << t)) a += wp[t];
+    } else {
+      a = wp[taps.kh[tap] * KW + taps.kw[tap]];
+    }
+    v[kk] = a;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  reinterpret_cast<uint4*>(dst)[id] = o;
+}
+
+cudaError_t launch_pack_weights(const float* w, int cout, int cin_total, int KH, int KW, int cin_off, int ksteps,
+                                const PackTaps& taps, __nv_bfloat16* dst, cudaStream_t s) {
+  const long long nvec = (long long)(cout / 128) * ksteps * taps.ntaps * 256;
+  const int threads = 256;
+  const long long blocks = (nvec + threads - 1) / threads;
+  pack_weights_kernel<<<(unsigned)blocks, threads, 0, s>>>(w, cout, cin_total, KH, KW, cin_off, ksteps, taps, dst, nvec);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ GroupNorm apply
+constexpr int GN_PLANES_PER_CTA = 4;
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
+  extern __shared__ float gsm[];  // scale[Ct], shift[Ct], mean[groups], rstd[groups]
+  const int Ct = p.C[0] + p.C[1];
+  float* scale = gsm;
+  float* shift = gsm + Ct;
+  float* gmean = gsm + 2 * Ct;
+  float* grstd = gmean + p.groups;
+  const int n = blockIdx.z;
+  const int cpg = Ct / p.groups;
+  const Geom g = make_geom(p.N, p.H, p.W);
+  for (int gi = threadIdx.x; gi < p.groups; gi += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int c = gi * cpg; c < (gi + 1) * cpg; c += 4) {
+      const float* st = (c < p.C[0]) ? p.stats[0] + ((long long)n * (p.C[0] >> 2) + (c >> 2)) * 2
+                                     : p.stats[1] + ((long long)n * (p.C[1] >> 2) + ((c - p.C[0]) >> 2)) * 2;
+      s += st[0];
+      q += st[1];
+    }
+    const float cnt = (float)cpg * (float)p.H * (float)p.W;
+    const float mean = s / cnt;
+    const float var = fmaxf(q / cnt - mean * mean, 0.f);
+    gmean[gi] = mean;
+    grstd[gi] = rsqrtf(var + p.eps);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Ct; c += blockDim.x) {
+    const int gi = c / cpg;
+    const float sc = p.gamma[c] * grstd[gi];
+    scale[c] = sc;
+    shift[c] = p.beta[c] - gmean[gi] * sc;
+  }
+  __syncthreads();
+
+  const int pidx = blockIdx.x * blockDim.x + threadIdx.x;  // valid-pixel index
+  if (pidx >= p.H * p.W) return;
+  const int h = pidx / p.W, w = pidx - h * p.W;
+  const long long pix = (long long)(g.lead + h * g.Wp + w) * 8;
+  const int pl0 = blockIdx.y * GN_PLANES_PER_CTA;
+  const int planes0 = p.C[0] >> 3;
+  uint4 in[GN_PLANES_PER_CTA];
+#pragma unroll
+  for (int k = 0; k < GN_PLANES_PER_CTA; ++k) {
+    const int pl = pl0 + k;
+    const __nv_bfloat16* sp = (pl < planes0)
+        ? p.src[0] + ((long long)n * planes0 + pl) * g.PL * 8
+        : p.src[1] + ((long long)n * (p.C[1] >> 3) + (pl - planes0)) * g.PL * 8;
+    in[k] = *reinterpret_cast<const uint4*>(sp + pix);
+  }
+#pragma unroll
+  for (int k = 0; k < GN_PLANES_PER_CTA; ++k) {
+    const int pl = pl0 + k;
+    const int c0 = pl * 8;
+    const uint32_t u[4] = {in[k].x, in[k].y, in[k].z, in[k].w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 f = unpack_bf16x2(u[e]);
+      float a = f.x * scale[c0 + 2 * e] + shift[c0 + 2 * e];
+      float b = f.y * scale[c0 + 2 * e + 1] + shift[c0 + 2 * e + 1];
+      if (p.silu) { a = silu_f(a); b = silu_f(b); }
+      o[e] = pack_bf16x2(a, b);
+    }
+    __nv_bfloat16* dp = p.dst + ((long long)n * (Ct >> 3) + pl) * g.PL * 8;
+    *reinterpret_cast<uint4*>(dp + pix) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+cudaError_t launch_gn_apply(const GnApplyParams& p, cudaStream_t s) {
+  const int Ct = p.C[0] + p.C[1];
+  dim3 grid((p.H * p.W + 255) / 256, (Ct >> 3) / GN_PLANES_PER_CTA, p.N);
+  const size_t smem = (2 * Ct + 2 * p.groups) * sizeof(float);
+  gn_apply_kernel<<<grid, 256, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ conv_in
+__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ b, int N, int cin, int H, int W,
+                                                      int cout, __nv_bfloat16* __restrict__ out,
+                                                      float* __restrict__ stats) {
+  __shared__ float red[8][4];
+  const Geom g = make_geom(N, H, W);
+  const int n = blockIdx.z, pl = blockIdx.y;
+  const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = pidx < H * W;
+  const int h = valid ? pidx / W : 0, ww = valid ? pidx - h * W : 0;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = b[pl * 8 + e];
+  for (int ci = 0; ci < cin; ++ci) {
+    const float* xi = x + ((long long)n * cin + ci) * H * W;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hh = h + kh - 1;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wx = ww + kw - 1;
+        const float xv = (valid && hh >= 0 && hh < H && wx >= 0 && wx < W) ? xi[hh * W + wx] : 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          acc[e] = fmaf(xv, __ldg(w + (((long long)(pl * 8 + e) * cin + ci) * 3 + kh) * 3 + kw), acc[e]);
+      }
+    }
+  }
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (valid) {
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+    __nv_bfloat16* dp = out + ((long long)n * (cout >> 3) + pl) * g.PL * 8 + (long long)(g.lead + h * g.Wp + ww) * 8;
+    *reinterpret_cast<uint4*>(dp) = o;
+    s4[0] = acc[0] + acc[1] + acc[2] + acc[3];
+    s4[1] = acc[0] * acc[0] + acc[1] * acc[1] + acc[2] * acc[2] + acc[3] * acc[3];
+    s4[2] = acc[4] + acc[5] + acc[6] + acc[7];
+    s4[3] = acc[4] * acc[4] + acc[5] * acc[5] + acc[6] * acc[6] + acc[7] * acc[7];
+  }
+  if (stats) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int sh = 16; sh >= 1; sh >>= 1) s4[k] += __shfl_xor_sync(0xffffffffu, s4[k], sh);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[warp][0] = s4[0]; red[warp][1] = s4[1]; red[warp][2] = s4[2]; red[warp][3] = s4[3]; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      float t = 0.f;
+      for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+      // quads 2*pl (values 0,1) and 2*pl+1 (values 2,3)
+      float* dst = stats + ((long long)n * (cout >> 2) + pl * 2 + (threadIdx.x >> 1)) * 2 + (threadIdx.x & 1);
+      atomicAdd(dst, t);
+    }
+  }
+}
+
+cudaError_t launch_conv_in(const float* x, const float* w, const float* b, int N, int cin, int H, int W, int cout,
+                           __nv_bfloat16* out, float* stats, cudaStream_t s) {
+  dim3 grid((H * W + 255) / 256, cout >> 3, N);
+  conv_in_kernel<<<grid, 256, 0, s>>>(x, w, b, N, cin, H, W, cout, out, stats);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------- conv_norm_out + SiLU + conv_out + scheduler step
+constexpr int CO_TILE = 16;
+constexpr int CO_HALO = CO_TILE + 2;
+constexpr int CO_MAXOUT = 4;
+
+__global__ void __launch_bounds__(256) conv_out_kernel(const ConvOutParams p) {
+  extern __shared__ __align__(16) uint8_t osm[];
+  const int planes = p.C >> 3;
+  uint4* act = reinterpret_cast<uint4*>(osm);                                   // [planes][324] 16 B vectors
+  float* wsm = reinterpret_cast<float*>(osm + (size_t)planes * CO_HALO * CO_HALO * 16);  // [cout][9][C]
+  float* scale = wsm + p.cout * 9 * p.C;
+  float* shift = scale + p.C;
+  float* gmean = shift + p.C;
+  float* grstd = gmean + p.groups;
+  const Geom g = make_geom(p.N, p.H, p.W);
+  const int n = blockIdx.z;
+  const int h0 = blockIdx.y * CO_TILE, w0 = blockIdx.x * CO_TILE;
+  const int cpg = p.C / p.groups;
+
+  for (int gi = threadIdx.x; gi < p.groups; gi += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int c = gi * cpg; c < (gi + 1) * cpg; c += 4) {
+      const float* st = p.stats + ((long long)n * (p.C >> 2) + (c >> 2)) * 2;
+      s += st[0];
+      q += st[1];
+    }
+    const float cnt = (float)cpg * (float)p.H * (float)p.W;
+    const float mean = s / cnt;
+    gmean[gi] = mean;
+    grstd[gi] = rsqrtf(fmaxf(q / cnt - mean * mean, 0.f) + p.eps);
+  }
+  // weights: fp32 [cout][C][3][3] -> smem [cout][tap][C]
+  for (int i = threadIdx.x; i < p.cout * p.C * 9; i += blockDim.x) {
+    const int co = i / (p.C * 9);
+    const int rem = i - co * p.C * 9;
+    const int c = rem / 9, t = rem - c * 9;
+    wsm[(co * 9 + t) * p.C + c] = p.w[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    const int gi = c / cpg;
+    const float sc = p.gamma[c] * grstd[gi];
+    scale[c] = sc;
+    shift[c] = p.beta[c] - gmean[gi] * sc;
+  }
+  __syncthreads();
+  // normalised + SiLU halo tile (zero outside the image: the conv pads the *activated* tensor)
+  const __nv_bfloat16* img = p.src + (long long)n * planes * g.PL * 8;
+  for (int i = threadIdx.x; i < planes * CO_HALO * CO_HALO; i += blockDim.x) {
+    const int pl = i / (CO_HALO * CO_HALO);
+    const int hp = i - pl * CO_HALO * CO_HALO;
+    const int hy = hp / CO_HALO, hx = hp - hy * CO_HALO;
+    const int h = h0 + hy - 1, w = w0 + hx - 1;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (h >= 0 && h < p.H && w >= 0 && w < p.W) {
+      const uint4 rv = *reinterpret_cast<const uint4*>(img + ((long long)pl * g.PL + g.lead + h * g.Wp + w) * 8);
+      const uint32_t u[4] = {rv.x, rv.y, rv.z, rv.w};
+      uint32_t r[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16x2(u[e]);
+        const int c = pl * 8 + 2 * e;
+        r[e] = pack_bf16x2(silu_f(f.x * scale[c] + shift[c]), silu_f(f.y * scale[c + 1] + shift[c + 1]));
+      }
+      o = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+    act[i] = o;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float acc[CO_MAXOUT];
+#pragma unroll
+  for (int co = 0; co < CO_MAXOUT; ++co) acc[co] = 0.f;
+  for (int pl = 0; pl < planes; ++pl) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int kh = t / 3, kw = t - kh * 3;
+      const uint4 a = act[pl * CO_HALO * CO_HALO + (ty + kh) * CO_HALO + tx + kw];
+      float av[8];
+      float2 f;
+      f = unpack_bf16x2(a.x); av[0] = f.x; av[1] = f.y;
+      f = unpack_bf16x2(a.y); av[2] = f.x; av[3] = f.y;
+      f = unpack_bf16x2(a.z); av[4] = f.x; av[5] = f.y;
+      f = unpack_bf16x2(a.w); av[6] = f.x; av[7] = f.y;
+#pragma unroll
+      for (int co = 0; co < CO_MAXOUT; ++co) {
+        if (co < p.cout) {
+          const float4* wp = reinterpret_cast<const float4*>(wsm + (co * 9 + t) * p.C + pl * 8);
+          const float4 w0v = wp[0], w1v = wp[1];
+          acc[co] += av[0] * w0v.x + av[1] * w0v.y + av[2] * w0v.z + av[3] * w0v.w +
+                     av[4] * w1v.x + av[5] * w1v.y + av[6] * w1v.z + av[7] * w1v.w;
+        }
+      }
+    }
+  }
+  const int h = h0 + ty, w = w0 + tx;
+  if (h < p.H && w < p.W) {
+#pragma unroll
+    for (int co = 0; co < CO_MAXOUT; ++co) {
+      if (co < p.cout) {
+        const float e = acc[co] + p.b[co];
+        const long long idx = (((long long)n * p.cout + co) * p.H + h) * p.W + w;
+        if (p.eps_out) p.eps_out[idx] = e;
+        if (p.x_out) {
+          const float xv = p.x[idx];
+          float x0 = (xv - p.coef.sqrt_1m_at * e) * p.coef.inv_sqrt_at;
+          if (p.coef.do_clip) x0 = fminf(fmaxf(x0, -p.coef.clip), p.coef.clip);
+          float r = p.coef.c_x0 * x0 + p.coef.c_xt * xv + p.coef.c_eps * e;
+          if (p.z) r += p.coef.c_z * p.z[idx];
+          p.x_out[idx] = r;
+        }
+      }
+    }
+  }
+}
+
+cudaError_t launch_conv_out(const ConvOutParams& p, cudaStream_t s) {
+  if (p.cout > CO_MAXOUT) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(p.C >> 3) * CO_HALO * CO_HALO * 16 +
+                      ((size_t)p.cout * 9 * p.C + 2 * p.C + 2 * p.groups) * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    smem_set = smem;
+  }
+  dim3 grid((p.W + CO_TILE - 1) / CO_TILE, (p.H + CO_TILE - 1) / CO_TILE, p.N);
+  conv_out_kernel<<<grid, 256, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ resampling
+__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int C,
+                                  int H, int W) {
+  const Geom gi = make_geom(N, H, W), go = make_geom(N, 2 * H, 2 * W);
+  const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pidx >= 4 * H * W) return;
+  const int ho = pidx / (2 * W), wo = pidx - ho * 2 * W;
+  const long long plane = (long long)blockIdx.z * (C >> 3) + blockIdx.y;
+  const uint4 v = *reinterpret_cast<const uint4*>(src + (plane * gi.PL + gi.lead + (ho >> 1) * gi.Wp + (wo >> 1)) * 8);
+  *reinterpret_cast<uint4*>(dst + (plane * go.PL + go.lead + ho * go.Wp + wo) * 8) = v;
+}
+cudaError_t launch_upsample2x(const __nv_bfloat16* src, __nv_bfloat16* dst, int N, int C, int H, int W, cudaStream_t s) {
+  dim3 grid((4 * H * W + 255) / 256, C >> 3, N);
+  upsample2x_kernel<<<grid, 256, 0, s>>>(src, dst, N, C, H, W);
+  return cudaGetLastError();
+}
+
+// dst4: four PF8 tensors (N, C, H/2, W/2) back to back, index a*2+b holds x[2h'+a, 2w'+b]
+__global__ void parity_split_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst4, int N,
+                                    int C, int H, int W) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const Geom gi = make_geom(N, H, W), go = make_geom(N, Ho, Wo);
+  const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pidx >= Ho * Wo) return;
+  const int ho = pidx / Wo, wo = pidx - ho * Wo;
+  const long long plane = (long long)blockIdx.z * (C >> 3) + blockIdx.y;
+  const long long tsz = (long long)N * (C >> 3) * go.PL * 8;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const uint4 v = *reinterpret_cast<const uint4*>(
+          src + (plane * gi.PL + gi.lead + (2 * ho + a) * gi.Wp + 2 * wo + b) * 8);
+      *reinterpret_cast<uint4*>(dst4 + (a * 2 + b) * tsz + (plane * go.PL + go.lead + ho * go.Wp + wo) * 8) = v;
+    }
+}
+cudaError_t launch_parity_split(const __nv_bfloat16* src, __nv_bfloat16* dst4, int N, int C, int H, int W, cudaStream_t s) {
+  dim3 grid(((H / 2) * (W / 2) + 255) / 256, C >> 3, N);
+  parity_split_kernel<<<grid, 256, 0, s>>>(src, dst4, N, C, H, W);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ layout conversion
+__global__ void nchw_to_pf8_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int C, int H, int W) {
+  const Geom g = make_geom(N, H, W);
+  const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pidx >= H * W) return;
+  const int h = pidx / W, w = pidx - h * W;
+  const int pl = blockIdx.y, n = blockIdx.z;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = src[(((long long)n * C + pl * 8 + e) * H + h) * W + w];
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(dst + (((long long)n * (C >> 3) + pl) * g.PL + g.lead + h * g.Wp + w) * 8) = o;
+}
+cudaError_t launch_nchw_to_pf8(const float* src, __nv_bfloat16* dst, int N, int C, int H, int W, cudaStream_t s) {
+  dim3 grid((H * W + 255) / 256, C >> 3, N);
+  nchw_to_pf8_kernel<<<grid, 256, 0, s>>>(src, dst, N, C, H, W);
+  return cudaGetLastError();
+}
+__global__ void pf8_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int N, int C, int H, int W) {
+  const Geom g = make_geom(N, H, W);
+  const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pidx >= H * W) return;
+  const int h = pidx / W, w = pidx - h * W;
+  const int pl = blockIdx.y, n = blockIdx.z;
+  const uint4 v = *reinterpret_cast<const uint4*>(src + (((long long)n * (C >> 3) + pl) * g.PL + g.lead + h * g.Wp + w) * 8);
+  const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = unpack_bf16x2(u[e]);
+    dst[(((long long)n * C + pl * 8 + 2 * e) * H + h) * W + w] = f.x;
+    dst[(((long long)n * C + pl * 8 + 2 * e + 1) * H + h) * W + w] = f.y;
+  }
+}
+cudaError_t launch_pf8_to_nchw(const __nv_bfloat16* src, float* dst, int N, int C, int H, int W, cudaStream_t s) {
+  dim3 grid((H * W + 255) / 256, C >> 3, N);
+  pf8_to_nchw_kernel<<<grid, 256, 0, s>>>(src, dst, N, C, H, W);
+  return cudaGetLastError();
+}
+
+
+// ------------------------------------------------------------------------------------ standalone quad stats
+// (the hot path gets these from the producing conv's epilogue; this kernel serves tensors that arrive from
+// outside, e.g. the op-level GroupNorm entry point)
+__global__ void __launch_bounds__(256) quad_stats_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ stats,
+                                                         int N, int C, int H, int W) {
+  __shared__ float red[8][4];
+  const Geom g = make_geom(N, H, W);
+  const int pl = blockIdx.y, n = blockIdx.z;
+  const __nv_bfloat16* sp = src + ((long long)n * (C >> 3) + pl) * g.PL * 8;
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int pidx = blockIdx.x * blockDim.x + threadIdx.x; pidx < H * W; pidx += gridDim.x * blockDim.x) {
+    const int h = pidx / W, w = pidx - h * W;
+    const uint4 v = *reinterpret_cast<const uint4*>(sp + (long long)(g.lead + h * g.Wp + w) * 8);
+    float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+    s4[0] += a.x + a.y + b.x + b.y;
+    s4[1] += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
+    s4[2] += c.x + c.y + d.x + d.y;
+    s4[3] += c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int sh = 16; sh >= 1; sh >>= 1) s4[k] += __shfl_xor_sync(0xffffffffu, s4[k], sh);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[warp][0] = s4[0]; red[warp][1] = s4[1]; red[warp][2] = s4[2]; red[warp][3] = s4[3]; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    atomicAdd(stats + ((long long)n * (C >> 2) + pl * 2 + (threadIdx.x >> 1)) * 2 + (threadIdx.x & 1), t);
+  }
+}
+cudaError_t launch_quad_stats(const __nv_bfloat16* src, float* stats, int N, int C, int H, int W, cudaStream_t s) {
+  int bx = (H * W + 255) / 256;
+  if (bx > 64) bx = 64;
+  dim3 grid(bx, C >> 3, N);
+  quad_stats_kernel<<<grid, 256, 0, s>>>(src, stats, N, C, H, W);
+  return cudaGetLastError();
+}
+
+// pipeline_audio_diffusion.py:192-194: (x/2+0.5).clamp(0,1) -> *255 -> numpy round (half to even) -> uint8
+__global__ void sample_to_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ img, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = __fadd_rn(__fdiv_rn(x[i], 2.0f), 0.5f);
+  v = fminf(fmaxf(v, 0.0f), 1.0f);
+  img[i] = (uint8_t)__float2int_rn(__fmul_rn(v, 255.0f));
+}
+cudaError_t launch_sample_to_u8(const float* x, uint8_t* img, size_t n, cudaStream_t s) {
+  sample_to_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, img, n);
+  return cudaGetLastError();
+}
+
+}  // namespace b200ad

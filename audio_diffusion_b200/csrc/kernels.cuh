@@ -1,0 +1,84 @@
+// Launchers of the non-tensor-core kernels of the U-Net path (elementwise.cu, attention.cu, temb.cu).
+#pragma once
+#include "common.cuh"
+
+namespace b200ad {
+
+// weights fp32 [cout][cin_total][KH][KW]  ->  packed bf16 blocks [cout/128][ksteps][ntaps][2][16][8][8]
+// for input channels [cin_off, cin_off + 16*ksteps) and the listed (kh, kw) taps.
+// If fold != 0 the tap list is interpreted as groups: tap t sums the source taps whose bit is set in
+// fold_mask[t] (bit kh*KW+kw) — used to fold nearest-2x upsampling into the conv weights.
+struct PackTaps {
+  int ntaps;
+  int kh[9], kw[9];
+  unsigned fold_mask[9];
+  int fold;
+};
+cudaError_t launch_pack_weights(const float* w, int cout, int cin_total, int KH, int KW, int cin_off, int ksteps,
+                                const PackTaps& taps, __nv_bfloat16* dst, cudaStream_t s);
+
+// GroupNorm (+ optional SiLU) apply over the channel concatenation of up to two raw PF8 sources.
+// stats: running (sum, sumsq) per (n, 4-channel quad) written by the producers' epilogues.
+struct GnApplyParams {
+  const __nv_bfloat16* src[2];
+  const float* stats[2];      // [N][C_i/4][2]
+  int C[2];                   // channels of each source (C[1] = 0 if single)
+  const float* gamma;         // [C0 + C1]
+  const float* beta;
+  __nv_bfloat16* dst;         // PF8 with C0 + C1 channels
+  int N, H, W, groups;
+  float eps;
+  int silu;
+};
+cudaError_t launch_gn_apply(const GnApplyParams& p, cudaStream_t s);
+
+// conv_in: fp32 NCHW (N, cin, H, W), 3x3 pad 1 -> raw bf16 PF8 (cout channels) + quad stats.
+cudaError_t launch_conv_in(const float* x, const float* w, const float* b, int N, int cin, int H, int W, int cout,
+                           __nv_bfloat16* out, float* stats, cudaStream_t s);
+
+// conv_norm_out + SiLU + conv_out (3x3, C -> cout small) fused with the scheduler update.
+// eps_out (optional): model output, fp32 NCHW.  If x_out != null:
+//   x0 = clamp((x - sqrt_1m_at * eps) * inv_sqrt_at, -clip, clip);  x_out = c_x0 * x0 + c_xt * x + c_eps * eps + c_z * z
+// which covers DDPM (c_eps = 0) and DDIM (c_xt = 0).
+struct StepCoef {
+  float sqrt_1m_at, inv_sqrt_at, clip, c_x0, c_xt, c_eps, c_z;
+  int do_clip;
+};
+struct ConvOutParams {
+  const __nv_bfloat16* src;   // raw PF8, C channels
+  const float* stats;         // [N][C/4][2]
+  const float* gamma;
+  const float* beta;
+  const float* w;             // fp32 [cout][C][3][3]
+  const float* b;             // [cout]
+  int N, C, H, W, cout, groups;
+  float eps;
+  float* eps_out;             // fp32 NCHW or null
+  const float* x;             // fp32 NCHW current sample (scheduler input) or null
+  const float* z;             // fp32 NCHW noise or null
+  float* x_out;               // fp32 NCHW or null
+  StepCoef coef;
+};
+cudaError_t launch_conv_out(const ConvOutParams& p, cudaStream_t s);
+
+// nearest 2x upsample PF8 (H, W) -> PF8 (2H, 2W); stride-2 parity split PF8 (H, W) -> 4 x PF8 (H/2, W/2)
+cudaError_t launch_upsample2x(const __nv_bfloat16* src, __nv_bfloat16* dst, int N, int C, int H, int W, cudaStream_t s);
+cudaError_t launch_parity_split(const __nv_bfloat16* src, __nv_bfloat16* dst4, int N, int C, int H, int W, cudaStream_t s);
+
+cudaError_t launch_quad_stats(const __nv_bfloat16* src, float* stats, int N, int C, int H, int W, cudaStream_t s);
+cudaError_t launch_sample_to_u8(const float* x, uint8_t* img, size_t n, cudaStream_t s);
+
+// layout conversion for tests / debugging
+cudaError_t launch_nchw_to_pf8(const float* src, __nv_bfloat16* dst, int N, int C, int H, int W, cudaStream_t s);
+cudaError_t launch_pf8_to_nchw(const __nv_bfloat16* src, float* dst, int N, int C, int H, int W, cudaStream_t s);
+
+// timestep embedding: t[N] -> sinusoid(dim0) -> linear1 -> SiLU -> linear2 -> SiLU = temb_act [N][4*dim0];
+// then all resnet projections at once: proj [N][rows] = Wcat [rows][4*dim0] * temb_act + bcat.
+cudaError_t launch_temb(const float* t, int N, int dim0, const float* w1, const float* b1, const float* w2,
+                        const float* b2, float* temb_act, const float* wcat, const float* bcat, int rows,
+                        float* proj, cudaStream_t s);
+
+// self-attention core on the fused qkv tensor (PF8, 3*C channels: q | k | v; head_dim 8 = one plane per head).
+cudaError_t launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int N, int C, int H, int W, cudaStream_t s);
+
+}  // namespace b200ad

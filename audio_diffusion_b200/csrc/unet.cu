@@ -1,0 +1,825 @@
+// Host side of the U-Net: parameter table (diffusers naming), weight packing, activation workspace layout and
+// the launch plan that walks UNet2DModel.forward (reference call sites: audiodiffusion/pipeline_audio_diffusion.py:163,
+// :237; architecture: scripts/train_unet.py:115-137).  No tensor math happens on the host.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b200ad.h"
+#include "conv_tc.cuh"
+#include "kernels.cuh"
+
+namespace b200ad {
+
+thread_local char g_err[512] = "";
+int set_err(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return -1;
+}
+#define CK(call)                                                                  \
+  do {                                                                            \
+    cudaError_t e__ = (call);                                                     \
+    if (e__ != cudaSuccess) return set_err("%s: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+struct Param {
+  std::string name;
+  std::vector<int64_t> shape;
+};
+
+struct Act {  // PF8 activation tensor
+  __nv_bfloat16* p = nullptr;
+  int C = 0, H = 0, W = 0;
+  float* stats = nullptr;
+};
+
+enum OpKind { OP_TEMB, OP_CONV_IN, OP_GN, OP_CONV, OP_UPSAMPLE, OP_PARITY, OP_ATTN, OP_CONV_OUT };
+struct Op {
+  OpKind kind;
+  ConvParams conv;
+  GnApplyParams gn;
+  // generic slots
+  const __nv_bfloat16* src = nullptr;
+  __nv_bfloat16* dst = nullptr;
+  int C = 0, H = 0, W = 0;
+  ConvOutParams co;
+};
+
+struct Bump {  // two-pass bump allocator: base == nullptr computes sizes only
+  uint8_t* base = nullptr;
+  size_t off = 0;
+  void* take(size_t bytes) {
+    off = (off + 255) & ~(size_t)255;
+    void* r = base ? base + off : nullptr;
+    off += bytes;
+    return r;
+  }
+};
+
+struct PackJob {  // one K-segment's packed weights
+  int w_param;      // index of the fp32 weight in the table
+  int cout, cin_total, KH, KW, cin_off, ksteps;
+  PackTaps taps;
+  size_t off;       // byte offset in the packed arena
+};
+
+}  // namespace b200ad
+
+using namespace b200ad;
+
+struct b200ad_unet {
+  b200ad_unet_config cfg;
+  std::vector<Param> params;
+  std::map<std::string, int> pidx;
+  std::vector<const float*> pptr;
+  // packed arena layout
+  std::vector<PackJob> jobs;
+  std::map<std::string, size_t> seg_off;  // "<conv name>#<seg>" -> byte offset
+  size_t packed_bytes = 0;
+  size_t off_wcat = 0, off_bcat = 0, off_misc = 0;
+  std::map<std::string, size_t> misc_off;  // fused bias vectors (floats)
+  int temb_rows = 0;
+  std::map<std::string, int> temb_row_off;
+  uint8_t* packed = nullptr;
+  // workspace / plan
+  int N = 0, H = 0, W = 0;
+  uint8_t* ws = nullptr;
+  size_t ws_bytes = 0;
+  std::vector<Op> plan;
+  std::map<std::string, Act> taps;
+  float* stats_arena = nullptr;
+  size_t stats_bytes = 0;
+  float* temb_act = nullptr;
+  float* temb_proj = nullptr;
+  int num_sms = 148;
+  int last_launches = 0;
+};
+
+namespace b200ad {
+
+// ------------------------------------------------------------------------------ parameter table
+static void add_param(b200ad_unet* h, const std::string& name, std::vector<int64_t> shape) {
+  h->pidx[name] = (int)h->params.size();
+  h->params.push_back({name, std::move(shape)});
+}
+static void p_conv(b200ad_unet* h, const std::string& n, int cin, int cout, int k) {
+  add_param(h, n + ".weight", {cout, cin, k, k});
+  add_param(h, n + ".bias", {cout});
+}
+static void p_lin(b200ad_unet* h, const std::string& n, int cin, int cout) {
+  add_param(h, n + ".weight", {cout, cin});
+  add_param(h, n + ".bias", {cout});
+}
+static void p_gn(b200ad_unet* h, const std::string& n, int c) {
+  add_param(h, n + ".weight", {c});
+  add_param(h, n + ".bias", {c});
+}
+static void p_resnet(b200ad_unet* h, const std::string& n, int cin, int cout, int temb) {
+  p_gn(h, n + ".norm1", cin);
+  p_conv(h, n + ".conv1", cin, cout, 3);
+  p_lin(h, n + ".time_emb_proj", temb, cout);
+  p_gn(h, n + ".norm2", cout);
+  p_conv(h, n + ".conv2", cout, cout, 3);
+  if (cin != cout) p_conv(h, n + ".conv_shortcut", cin, cout, 1);
+}
+static void p_attn(b200ad_unet* h, const std::string& n, int c) {
+  p_gn(h, n + ".group_norm", c);
+  p_lin(h, n + ".to_q", c, c);
+  p_lin(h, n + ".to_k", c, c);
+  p_lin(h, n + ".to_v", c, c);
+  p_lin(h, n + ".to_out.0", c, c);
+}
+
+static std::string S(const char* fmt, ...) {
+  char buf[256];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  return buf;
+}
+
+static void build_param_table(b200ad_unet* h) {
+  const b200ad_unet_config& c = h->cfg;
+  const int nb = c.num_blocks, temb = c.block_out_channels[0] * 4;
+  p_conv(h, "conv_in", c.in_channels, c.block_out_channels[0], 3);
+  p_lin(h, "time_embedding.linear_1", c.block_out_channels[0], temb);
+  p_lin(h, "time_embedding.linear_2", temb, temb);
+  int out_c = c.block_out_channels[0];
+  for (int i = 0; i < nb; ++i) {
+    int in_c = out_c;
+    out_c = c.block_out_channels[i];
+    for (int j = 0; j < c.layers_per_block; ++j) {
+      p_resnet(h, S("down_blocks.%d.resnets.%d", i, j), j == 0 ? in_c : out_c, out_c, temb);
+      if (c.down_attn[i]) p_attn(h, S("down_blocks.%d.attentions.%d", i, j), out_c);
+    }
+    if (i != nb - 1) p_conv(h, S("down_blocks.%d.downsamplers.0.conv", i), out_c, out_c, 3);
+  }
+  const int mid = c.block_out_channels[nb - 1];
+  p_resnet(h, "mid_block.resnets.0", mid, mid, temb);
+  p_attn(h, "mid_block.attentions.0", mid);
+  p_resnet(h, "mid_block.resnets.1", mid, mid, temb);
+  out_c = c.block_out_channels[nb - 1];
+  for (int i = 0; i < nb; ++i) {
+    const int prev_c = out_c;
+    out_c = c.block_out_channels[nb - 1 - i];
+    const int in_c = c.block_out_channels[nb - 1 - (i + 1 < nb ? i + 1 : nb - 1)];
+    const int n = c.layers_per_block + 1;
+    for (int j = 0; j < n; ++j) {
+      const int skip_c = (j == n - 1) ? in_c : out_c;
+      const int res_in = (j == 0) ? prev_c : out_c;
+      p_resnet(h, S("up_blocks.%d.resnets.%d", i, j), res_in + skip_c, out_c, temb);
+      if (c.up_attn[i]) p_attn(h, S("up_blocks.%d.attentions.%d", i, j), out_c);
+    }
+    if (i != nb - 1) p_conv(h, S("up_blocks.%d.upsamplers.0.conv", i), out_c, out_c, 3);
+  }
+  p_gn(h, "conv_norm_out", c.block_out_channels[0]);
+  p_conv(h, "conv_out", c.block_out_channels[0], c.out_channels, 3);
+}
+
+// ------------------------------------------------------------------------------ packed-arena layout
+static PackTaps taps_3x3() {
+  PackTaps t{};
+  t.ntaps = 9;
+  for (int k = 0; k < 9; ++k) { t.kh[k] = k / 3; t.kw[k] = k % 3; }
+  return t;
+}
+static PackTaps taps_1x1() {
+  PackTaps t{};
+  t.ntaps = 1;
+  t.kh[0] = 0; t.kw[0] = 0;
+  return t;
+}
+// stride-2 3x3 conv on parity plane (a, b): the taps that read input rows of parity a and columns of parity b
+static PackTaps taps_parity(int a, int b) {
+  PackTaps t{};
+  t.ntaps = 0;
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw) {
+      const int pa = (kh == 1) ? 0 : 1, pb = (kw == 1) ? 0 : 1;
+      if (pa == a && pb == b) { t.kh[t.ntaps] = kh; t.kw[t.ntaps] = kw; ++t.ntaps; }
+    }
+  return t;
+}
+
+static void add_job(b200ad_unet* h, Bump& b, const std::string& key, const std::string& wname, int cout, int cin_total,
+                    int K, int cin_off, int cin_cnt, const PackTaps& taps) {
+  PackJob j;
+  j.w_param = h->pidx.at(wname);
+  j.cout = cout; j.cin_total = cin_total; j.KH = K; j.KW = K; j.cin_off = cin_off; j.ksteps = cin_cnt / 16;
+  j.taps = taps;
+  const size_t bytes = (size_t)(cout / 128) * j.ksteps * taps.ntaps * CONV_B_TAP;
+  b.take(0);
+  j.off = (b.off + 255) & ~(size_t)255;
+  b.take(bytes);
+  h->seg_off[key] = j.off;
+  h->jobs.push_back(j);
+}
+
+static void build_packed_layout(b200ad_unet* h) {
+  const b200ad_unet_config& c = h->cfg;
+  const int nb = c.num_blocks;
+  Bump b;
+  b.base = nullptr;
+  h->jobs.clear();
+  h->temb_rows = 0;
+  // NOTE: Bump with base == nullptr returns nullptr from take(); offsets are tracked via b.off.
+  auto take_off = [&](size_t bytes) { b.take(0); size_t o = (b.off + 255) & ~(size_t)255; b.take(bytes); return o; };
+  int out_c = c.block_out_channels[0];
+  std::vector<int> skip_c{out_c};
+  auto resnet = [&](const std::string& n, int ca, int cb, int co) {
+    const int cin = ca + cb;
+    add_job(h, b, n + ".conv1#0", n + ".conv1.weight", co, cin, 3, 0, cin, taps_3x3());
+    add_job(h, b, n + ".conv2#0", n + ".conv2.weight", co, co, 3, 0, co, taps_3x3());
+    if (cin != co) {
+      add_job(h, b, n + ".conv2#1", n + ".conv_shortcut.weight", co, cin, 1, 0, ca, taps_1x1());
+      if (cb) add_job(h, b, n + ".conv2#2", n + ".conv_shortcut.weight", co, cin, 1, ca, cb, taps_1x1());
+      h->misc_off[n + ".bias2"] = take_off((size_t)co * 4);
+    }
+    h->temb_row_off[n] = h->temb_rows;
+    h->temb_rows += co;
+  };
+  auto attn = [&](const std::string& n, int ch) {
+    add_job(h, b, n + ".qkv#q", n + ".to_q.weight", ch, ch, 1, 0, ch, taps_1x1());
+    add_job(h, b, n + ".qkv#k", n + ".to_k.weight", ch, ch, 1, 0, ch, taps_1x1());
+    add_job(h, b, n + ".qkv#v", n + ".to_v.weight", ch, ch, 1, 0, ch, taps_1x1());
+    add_job(h, b, n + ".out#0", n + ".to_out.0.weight", ch, ch, 1, 0, ch, taps_1x1());
+    h->misc_off[n + ".bias_qkv"] = take_off((size_t)3 * ch * 4);
+  };
+  for (int i = 0; i < nb; ++i) {
+    const int in_c = out_c;
+    out_c = c.block_out_channels[i];
+    for (int j = 0; j < c.layers_per_block; ++j) {
+      resnet(S("down_blocks.%d.resnets.%d", i, j), j == 0 ? in_c : out_c, 0, out_c);
+      if (c.down_attn[i]) attn(S("down_blocks.%d.attentions.%d", i, j), out_c);
+      skip_c.push_back(out_c);
+    }
+    if (i != nb - 1) {
+      const std::string n = S("down_blocks.%d.downsamplers.0.conv", i);
+      for (int a = 0; a < 2; ++a)
+        for (int bb = 0; bb < 2; ++bb)
+          add_job(h, b, n + S("#%d", a * 2 + bb), n + ".weight", out_c, out_c, 3, 0, out_c, taps_parity(a, bb));
+      skip_c.push_back(out_c);
+    }
+  }
+  const int mid = c.block_out_channels[nb - 1];
+  resnet("mid_block.resnets.0", mid, 0, mid);
+  attn("mid_block.attentions.0", mid);
+  resnet("mid_block.resnets.1", mid, 0, mid);
+  out_c = mid;
+  for (int i = 0; i < nb; ++i) {
+    const int prev_c = out_c;
+    out_c = c.block_out_channels[nb - 1 - i];
+    const int n = c.layers_per_block + 1;
+    for (int j = 0; j < n; ++j) {
+      const int sc = skip_c.back();
+      skip_c.pop_back();
+      const int res_in = (j == 0) ? prev_c : out_c;
+      resnet(S("up_blocks.%d.resnets.%d", i, j), res_in, sc, out_c);
+      if (c.up_attn[i]) attn(S("up_blocks.%d.attentions.%d", i, j), out_c);
+    }
+    if (i != nb - 1) {
+      const std::string nm = S("up_blocks.%d.upsamplers.0.conv", i);
+      add_job(h, b, nm + "#0", nm + ".weight", out_c, out_c, 3, 0, out_c, taps_3x3());
+    }
+  }
+  const int D = c.block_out_channels[0] * 4;
+  h->off_wcat = take_off((size_t)h->temb_rows * D * 4);
+  h->off_bcat = take_off((size_t)h->temb_rows * 4);
+  h->packed_bytes = (b.off + 255) & ~(size_t)255;
+}
+
+// ------------------------------------------------------------------------------ small device helpers
+__global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) o[i] = a[i] + (b ? b[i] : 0.f);
+}
+
+}  // namespace b200ad
+
+// ================================================================================= C ABI: U-Net
+extern "C" const char* b200ad_last_error(void) { return g_err; }
+extern "C" int b200ad_version(void) { return 1; }
+
+extern "C" int b200ad_unet_create(const b200ad_unet_config* cfg, b200ad_unet** out) {
+  if (!cfg || !out) return set_err("null argument");
+  if (cfg->num_blocks < 1 || cfg->num_blocks > B200AD_MAX_BLOCKS) return set_err("num_blocks out of range");
+  if (cfg->attention_head_dim != 8) return set_err("only attention_head_dim == 8 is implemented");
+  for (int i = 0; i < cfg->num_blocks; ++i)
+    if (cfg->block_out_channels[i] % 128) return set_err("block_out_channels must be multiples of 128");
+  if (cfg->out_channels > 4) return set_err("out_channels > 4 not implemented");
+  b200ad_unet* h = new b200ad_unet();
+  h->cfg = *cfg;
+  build_param_table(h);
+  build_packed_layout(h);
+  h->pptr.assign(h->params.size(), nullptr);
+  *out = h;
+  return 0;
+}
+extern "C" void b200ad_unet_destroy(b200ad_unet* h) { delete h; }
+extern "C" int b200ad_unet_num_params(const b200ad_unet* h) { return (int)h->params.size(); }
+extern "C" const char* b200ad_unet_param_name(const b200ad_unet* h, int i) { return h->params[i].name.c_str(); }
+extern "C" int b200ad_unet_param_shape(const b200ad_unet* h, int i, int64_t* dims) {
+  const auto& s = h->params[i].shape;
+  for (size_t k = 0; k < s.size(); ++k) dims[k] = s[k];
+  return (int)s.size();
+}
+extern "C" size_t b200ad_unet_packed_bytes(const b200ad_unet* h) { return h->packed_bytes; }
+
+extern "C" int b200ad_unet_set_params(b200ad_unet* h, const float* const* params, void* packed, size_t packed_bytes,
+                                      void* stream) {
+  if (packed_bytes < h->packed_bytes) return set_err("packed buffer too small: %zu < %zu", packed_bytes, h->packed_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  for (size_t i = 0; i < h->params.size(); ++i) h->pptr[i] = params[i];
+  h->packed = (uint8_t*)packed;
+  for (const PackJob& j : h->jobs)
+    CK(launch_pack_weights(h->pptr[j.w_param], j.cout, j.cin_total, j.KH, j.KW, j.cin_off, j.ksteps, j.taps,
+                           (__nv_bfloat16*)(h->packed + j.off), st));
+  // fused bias vectors
+  for (const auto& kv : h->misc_off) {
+    const std::string& key = kv.first;
+    float* dst = (float*)(h->packed + kv.second);
+    if (key.size() > 6 && key.compare(key.size() - 6, 6, ".bias2") == 0) {
+      const std::string n = key.substr(0, key.size() - 6);
+      const int co = (int)h->params[h->pidx.at(n + ".conv2.bias")].shape[0];
+      add_vec_kernel<<<(co + 255) / 256, 256, 0, st>>>(h->pptr[h->pidx.at(n + ".conv2.bias")],
+                                                       h->pptr[h->pidx.at(n + ".conv_shortcut.bias")], dst, co);
+      CK(cudaGetLastError());
+    } else {  // ".bias_qkv"
+      const std::string n = key.substr(0, key.size() - 9);
+      const int c = (int)h->params[h->pidx.at(n + ".to_q.bias")].shape[0];
+      CK(cudaMemcpyAsync(dst, h->pptr[h->pidx.at(n + ".to_q.bias")], c * 4, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(dst + c, h->pptr[h->pidx.at(n + ".to_k.bias")], c * 4, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(dst + 2 * c, h->pptr[h->pidx.at(n + ".to_v.bias")], c * 4, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  // concatenated time_emb_proj weights / biases
+  const int D = h->cfg.block_out_channels[0] * 4;
+  for (const auto& kv : h->temb_row_off) {
+    const int co = (int)h->params[h->pidx.at(kv.first + ".time_emb_proj.bias")].shape[0];
+    CK(cudaMemcpyAsync(h->packed + h->off_wcat + (size_t)kv.second * D * 4,
+                       h->pptr[h->pidx.at(kv.first + ".time_emb_proj.weight")], (size_t)co * D * 4,
+                       cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(h->packed + h->off_bcat + (size_t)kv.second * 4,
+                       h->pptr[h->pidx.at(kv.first + ".time_emb_proj.bias")], (size_t)co * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+// ================================================================================= plan builder
+namespace b200ad {
+
+struct Builder {
+  b200ad_unet* h;
+  Bump ws;
+  Bump st;  // stats arena (floats, offsets in bytes)
+  std::vector<Op>* plan;
+  std::map<std::string, Act> pool;  // reusable transient buffers keyed by tag
+  int N;
+  bool nopool = false;  // B200AD_DEBUG_NOPOOL=1: every activation gets its own buffer (per-layer parity taps)
+
+  Act alloc(int C, int H, int W, bool stats) {
+    Act a;
+    a.C = C; a.H = H; a.W = W;
+    const Geom g = make_geom(N, H, W);
+    a.p = (__nv_bfloat16*)ws.take((size_t)N * (C / 8) * g.PL * 16);
+    if (stats) a.stats = (float*)st.take((size_t)N * (C / 4) * 2 * 4);
+    return a;
+  }
+  Act pooled(const std::string& tag, int C, int H, int W, bool stats) {
+    const std::string key = S("%s:%d:%d:%d", tag.c_str(), C, H, W);
+    if (nopool) return alloc(C, H, W, stats);
+    auto it = pool.find(key);
+    if (it == pool.end()) it = pool.emplace(key, alloc(C, H, W, false)).first;
+    Act a = it->second;
+    if (stats) a.stats = (float*)st.take((size_t)N * (C / 4) * 2 * 4);
+    return a;
+  }
+  const float* P(const std::string& name) const { return h->pptr[h->pidx.at(name)]; }
+  const __nv_bfloat16* WP(const std::string& key) const {
+    return h->packed ? (const __nv_bfloat16*)(h->packed + h->seg_off.at(key)) : nullptr;
+  }
+  const float* MISC(const std::string& key) const { return h->packed ? (const float*)(h->packed + h->misc_off.at(key)) : nullptr; }
+
+  void conv_common(ConvParams& p, const Act& out) {
+    const Geom g = make_geom(N, out.H, out.W);
+    p.N = N; p.H = out.H; p.W = out.W; p.Wp = g.Wp; p.lead = g.lead; p.PL = g.PL;
+    p.wide = (out.W % 128 == 0) ? 1 : 0;
+    p.groups_per_img = p.wide ? ((out.H + CONV_MAXG - 1) / CONV_MAXG) * (out.W / 128)
+                              : (out.H * g.Wp + CONV_MAXG * CONV_TM - 1) / (CONV_MAXG * CONV_TM);
+    p.cout = out.C;
+    p.ntiles_n = out.C / 128;
+    p.total_work = N * p.groups_per_img * p.ntiles_n;
+    p.out = out.p;
+    p.stats = out.stats;
+  }
+  static void seg_taps(ConvSeg& s, const PackTaps& t, bool parity, int a, int b) {
+    s.ntaps = t.ntaps;
+    s.ht = s.hb = s.hl = s.hr = 0;
+    for (int k = 0; k < t.ntaps; ++k) {
+      if (parity) {
+        s.dh[k] = (t.kh[k] == 0) ? -1 : 0;
+        s.dw[k] = (t.kw[k] == 0) ? -1 : 0;
+      } else if (t.ntaps == 9) {
+        s.dh[k] = (signed char)(t.kh[k] - 1);
+        s.dw[k] = (signed char)(t.kw[k] - 1);
+      } else {
+        s.dh[k] = 0; s.dw[k] = 0;
+      }
+      if (s.dh[k] < 0) s.ht = 1;
+      if (s.dh[k] > 0) s.hb = 1;
+      if (s.dw[k] < 0) s.hl = 1;
+      if (s.dw[k] > 0) s.hr = 1;
+    }
+    (void)a; (void)b;
+  }
+  void set_seg(ConvSeg& s, const __nv_bfloat16* src, int C, int H, int W, const __nv_bfloat16* wpack, const PackTaps& t,
+               bool parity = false) {
+    const Geom g = make_geom(N, H, W);
+    s.src = src;
+    s.wpack = wpack;
+    s.img_stride = (long long)(C / 8) * g.PL * 8;
+    s.ksteps = C / 16;
+    seg_taps(s, t, parity, 0, 0);
+  }
+
+  void gn(const Act& a, const Act* b, const std::string& norm, const Act& dst, bool silu) {
+    Op op{};
+    op.kind = OP_GN;
+    GnApplyParams& p = op.gn;
+    p.src[0] = a.p; p.stats[0] = a.stats; p.C[0] = a.C;
+    p.src[1] = b ? b->p : nullptr; p.stats[1] = b ? b->stats : nullptr; p.C[1] = b ? b->C : 0;
+    p.gamma = P(norm + ".weight"); p.beta = P(norm + ".bias");
+    p.dst = dst.p;
+    p.N = N; p.H = a.H; p.W = a.W; p.groups = h->cfg.norm_num_groups; p.eps = h->cfg.norm_eps; p.silu = silu ? 1 : 0;
+    plan->push_back(op);
+  }
+
+  // ResnetBlock2D on x = cat(a, b) (b optional) -> out (raw + stats)
+  Act resnet(const std::string& n, const Act& a, const Act* b, int cout, bool out_pooled, const std::string& out_tag) {
+    const int cin = a.C + (b ? b->C : 0);
+    const int H = a.H, W = a.W;
+    Act n1 = pooled("norm", cin, H, W, false);
+    gn(a, b, n + ".norm1", n1, true);
+    Act h1 = pooled("h1", cout, H, W, true);
+    {
+      Op op{};
+      op.kind = OP_CONV;
+      ConvParams& p = op.conv;
+      conv_common(p, h1);
+      p.nseg = 1;
+      set_seg(p.seg[0], n1.p, cin, H, W, WP(n + ".conv1#0"), taps_3x3());
+      p.bias = P(n + ".conv1.bias");
+      p.temb = h->temb_proj + h->temb_row_off.at(n);
+      p.temb_stride = h->temb_rows;
+      p.res = nullptr;
+      plan->push_back(op);
+    }
+    Act n2 = pooled("norm", cout, H, W, false);
+    gn(h1, nullptr, n + ".norm2", n2, true);
+    Act out = out_pooled ? pooled(out_tag, cout, H, W, true) : alloc(cout, H, W, true);
+    {
+      Op op{};
+      op.kind = OP_CONV;
+      ConvParams& p = op.conv;
+      conv_common(p, out);
+      p.nseg = 1;
+      set_seg(p.seg[0], n2.p, cout, H, W, WP(n + ".conv2#0"), taps_3x3());
+      p.temb = nullptr;
+      p.temb_stride = 0;
+      if (cin != cout) {
+        set_seg(p.seg[1], a.p, a.C, H, W, WP(n + ".conv2#1"), taps_1x1());
+        p.nseg = 2;
+        if (b) {
+          set_seg(p.seg[2], b->p, b->C, H, W, WP(n + ".conv2#2"), taps_1x1());
+          p.nseg = 3;
+        }
+        p.bias = MISC(n + ".bias2");
+        p.res = nullptr;
+      } else {
+        p.bias = P(n + ".conv2.bias");
+        p.res = a.p;
+      }
+      plan->push_back(op);
+    }
+    h->taps[n + ".h1"] = h1;
+    h->taps[n] = out;
+    return out;
+  }
+
+  Act attention(const std::string& n, const Act& x, bool out_pooled, const std::string& out_tag) {
+    const int C = x.C, H = x.H, W = x.W;
+    Act nx = pooled("norm", C, H, W, false);
+    gn(x, nullptr, n + ".group_norm", nx, false);
+    Act qkv = pooled("qkv", 3 * C, H, W, false);
+    {
+      Op op{};
+      op.kind = OP_CONV;
+      ConvParams& p = op.conv;
+      conv_common(p, qkv);
+      p.nseg = 1;
+      set_seg(p.seg[0], nx.p, C, H, W, WP(n + ".qkv#q"), taps_1x1());  // q|k|v blocks are contiguous
+      p.bias = MISC(n + ".bias_qkv");
+      p.temb = nullptr; p.temb_stride = 0; p.res = nullptr; p.stats = nullptr;
+      plan->push_back(op);
+    }
+    Act ao = pooled("attn_o", C, H, W, false);
+    {
+      Op op{};
+      op.kind = OP_ATTN;
+      op.src = qkv.p; op.dst = ao.p; op.C = C; op.H = H; op.W = W;
+      plan->push_back(op);
+    }
+    Act out = out_pooled ? pooled(out_tag, C, H, W, true) : alloc(C, H, W, true);
+    {
+      Op op{};
+      op.kind = OP_CONV;
+      ConvParams& p = op.conv;
+      conv_common(p, out);
+      p.nseg = 1;
+      set_seg(p.seg[0], ao.p, C, H, W, WP(n + ".out#0"), taps_1x1());
+      p.bias = P(n + ".to_out.0.bias");
+      p.temb = nullptr; p.temb_stride = 0;
+      p.res = x.p;
+      plan->push_back(op);
+    }
+    h->taps[n] = out;
+    return out;
+  }
+};
+
+static int build_plan(b200ad_unet* h, uint8_t* ws_base, int N, int H, int W, size_t* ws_bytes_out) {
+  const b200ad_unet_config& c = h->cfg;
+  const int nb = c.num_blocks;
+  std::vector<Op> plan;
+  Builder B;
+  B.h = h; B.N = N; B.plan = &plan;
+  {
+    const char* e = getenv("B200AD_DEBUG_NOPOOL");
+    B.nopool = e && e[0] == '1';
+  }
+  B.ws.base = ws_base;
+  // two-pass: the stats arena lives at the start of the workspace; its size is found by a dry run
+  size_t stats_bytes = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    plan.clear();
+    B.pool.clear();
+    h->taps.clear();
+    B.ws.off = 0;
+    B.st.off = 0;
+    B.st.base = ws_base;  // stats arena first
+    B.ws.off = (pass == 0) ? 0 : ((stats_bytes + 255) & ~(size_t)255);
+    if (pass == 0) B.st.base = nullptr;
+    const int D = c.block_out_channels[0] * 4;
+    h->temb_act = (float*)B.ws.take((size_t)N * D * 4);
+    h->temb_proj = (float*)B.ws.take((size_t)N * h->temb_rows * 4);
+    {
+      Op op{};
+      op.kind = OP_TEMB;
+      plan.push_back(op);
+    }
+    int out_c = c.block_out_channels[0];
+    int hh = H, ww = W;
+    Act x = B.alloc(out_c, hh, ww, true);
+    {
+      Op op{};
+      op.kind = OP_CONV_IN;
+      op.dst = x.p; op.C = out_c; op.H = hh; op.W = ww;
+      op.conv.stats = x.stats;
+      plan.push_back(op);
+    }
+    h->taps["conv_in"] = x;
+    std::vector<Act> skips{x};
+    for (int i = 0; i < nb; ++i) {
+      out_c = c.block_out_channels[i];
+      for (int j = 0; j < c.layers_per_block; ++j) {
+        const std::string rn = S("down_blocks.%d.resnets.%d", i, j);
+        if (c.down_attn[i]) {
+          Act r = B.resnet(rn, x, nullptr, out_c, true, "res_tmp");
+          x = B.attention(S("down_blocks.%d.attentions.%d", i, j), r, false, "");
+        } else {
+          x = B.resnet(rn, x, nullptr, out_c, false, "");
+        }
+        skips.push_back(x);
+      }
+      if (i != nb - 1) {
+        const std::string n = S("down_blocks.%d.downsamplers.0.conv", i);
+        const int Ho = hh / 2, Wo = ww / 2;
+        const Geom go = make_geom(N, Ho, Wo);
+        const size_t tsz = (size_t)N * (out_c / 8) * go.PL * 8;  // elements per parity tensor
+        Act par = B.pooled("parity", 4 * out_c, Ho, Wo, false);  // 4 tensors back to back (same bytes as 4C channels)
+        {
+          Op op{};
+          op.kind = OP_PARITY;
+          op.src = x.p; op.dst = par.p; op.C = out_c; op.H = hh; op.W = ww;
+          plan.push_back(op);
+        }
+        Act y = B.alloc(out_c, Ho, Wo, true);
+        {
+          Op op{};
+          op.kind = OP_CONV;
+          ConvParams& p = op.conv;
+          B.conv_common(p, y);
+          p.nseg = 4;
+          for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2; ++b)
+              B.set_seg(p.seg[a * 2 + b], par.p + (size_t)(a * 2 + b) * tsz, out_c, Ho, Wo,
+                        B.WP(n + S("#%d", a * 2 + b)), taps_parity(a, b), true);
+          p.bias = B.P(n + ".bias");
+          p.temb = nullptr; p.temb_stride = 0; p.res = nullptr;
+          plan.push_back(op);
+        }
+        h->taps[n] = y;
+        x = y;
+        hh = Ho; ww = Wo;
+        skips.push_back(x);
+      }
+    }
+    x = B.resnet("mid_block.resnets.0", x, nullptr, out_c, true, "res_tmp");
+    x = B.attention("mid_block.attentions.0", x, true, "up_a");
+    x = B.resnet("mid_block.resnets.1", x, nullptr, out_c, true, "up_b");
+    int flip = 0;
+    for (int i = 0; i < nb; ++i) {
+      out_c = c.block_out_channels[nb - 1 - i];
+      const int n = c.layers_per_block + 1;
+      for (int j = 0; j < n; ++j) {
+        Act sk = skips.back();
+        skips.pop_back();
+        const std::string rn = S("up_blocks.%d.resnets.%d", i, j);
+        if (c.up_attn[i]) {
+          Act r = B.resnet(rn, x, &sk, out_c, true, "res_tmp");
+          x = B.attention(S("up_blocks.%d.attentions.%d", i, j), r, true, (flip++ & 1) ? "up_b" : "up_a");
+        } else {
+          x = B.resnet(rn, x, &sk, out_c, true, (flip++ & 1) ? "up_b" : "up_a");
+        }
+      }
+      if (i != nb - 1) {
+        const std::string nm = S("up_blocks.%d.upsamplers.0.conv", i);
+        Act up = B.pooled("upsampled", out_c, hh * 2, ww * 2, false);
+        {
+          Op op{};
+          op.kind = OP_UPSAMPLE;
+          op.src = x.p; op.dst = up.p; op.C = out_c; op.H = hh; op.W = ww;
+          plan.push_back(op);
+        }
+        hh *= 2; ww *= 2;
+        Act y = B.pooled("up_conv", out_c, hh, ww, true);
+        {
+          Op op{};
+          op.kind = OP_CONV;
+          ConvParams& p = op.conv;
+          B.conv_common(p, y);
+          p.nseg = 1;
+          B.set_seg(p.seg[0], up.p, out_c, hh, ww, B.WP(nm + "#0"), taps_3x3());
+          p.bias = B.P(nm + ".bias");
+          p.temb = nullptr; p.temb_stride = 0; p.res = nullptr;
+          plan.push_back(op);
+        }
+        h->taps[nm] = y;
+        x = y;
+      }
+    }
+    {
+      Op op{};
+      op.kind = OP_CONV_OUT;
+      ConvOutParams& p = op.co;
+      p.src = x.p; p.stats = x.stats;
+      p.gamma = B.P("conv_norm_out.weight"); p.beta = B.P("conv_norm_out.bias");
+      p.w = B.P("conv_out.weight"); p.b = B.P("conv_out.bias");
+      p.N = N; p.C = x.C; p.H = hh; p.W = ww; p.cout = c.out_channels; p.groups = c.norm_num_groups; p.eps = c.norm_eps;
+      plan.push_back(op);
+    }
+    h->taps["pre_out"] = x;
+    if (pass == 0) stats_bytes = B.st.off;
+  }
+  if (ws_bytes_out) *ws_bytes_out = (B.ws.off + 255) & ~(size_t)255;
+  if (ws_base) {
+    h->plan = plan;
+    h->stats_arena = (float*)ws_base;
+    h->stats_bytes = stats_bytes;
+  }
+  return 0;
+}
+
+}  // namespace b200ad
+
+extern "C" size_t b200ad_unet_workspace_bytes(const b200ad_unet* hc, int N, int H, int W) {
+  b200ad_unet* h = const_cast<b200ad_unet*>(hc);
+  // dry run on a scratch copy of the mutable plan state
+  auto saved_plan = h->plan;
+  auto saved_taps = h->taps;
+  float* sa = h->stats_arena; size_t sb = h->stats_bytes; float* ta = h->temb_act; float* tp = h->temb_proj;
+  uint8_t* saved_packed = h->packed;
+  std::vector<const float*> saved_pptr = h->pptr;
+  size_t bytes = 0;
+  build_plan(h, nullptr, N, H, W, &bytes);
+  h->plan = saved_plan; h->taps = saved_taps; h->stats_arena = sa; h->stats_bytes = sb; h->temb_act = ta; h->temb_proj = tp;
+  h->packed = saved_packed; h->pptr = saved_pptr;
+  return bytes;
+}
+
+extern "C" int b200ad_unet_bind_workspace(b200ad_unet* h, void* workspace, size_t bytes, int N, int H, int W, void* stream) {
+  if (!h->packed) return set_err("set_params must be called before bind_workspace");
+  const int down = 1 << (h->cfg.num_blocks - 1);
+  if (H % down || W % down) return set_err("H and W must be multiples of %d", down);
+  size_t need = 0;
+  build_plan(h, nullptr, N, H, W, &need);
+  if (bytes < need) return set_err("workspace too small: %zu < %zu", bytes, need);
+  CK(cudaMemsetAsync(workspace, 0, need, (cudaStream_t)stream));
+  build_plan(h, (uint8_t*)workspace, N, H, W, &need);
+  h->N = N; h->H = H; h->W = W;
+  h->ws = (uint8_t*)workspace; h->ws_bytes = need;
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev));
+  return 0;
+}
+
+static int run_plan(b200ad_unet* h, const float* x, const float* t, const float* z, const b200ad_step_coef* coef,
+                    float* x_out, float* eps_out, cudaStream_t st) {
+  if (h->plan.empty()) return set_err("bind_workspace must be called before forward");
+  const b200ad_unet_config& c = h->cfg;
+  int launches = 0;
+  CK(cudaMemsetAsync(h->stats_arena, 0, h->stats_bytes, st));
+  for (Op& op : h->plan) {
+    switch (op.kind) {
+      case OP_TEMB: {
+        const int d0 = c.block_out_channels[0];
+        CK(launch_temb(t, h->N, d0, h->pptr[h->pidx.at("time_embedding.linear_1.weight")],
+                       h->pptr[h->pidx.at("time_embedding.linear_1.bias")],
+                       h->pptr[h->pidx.at("time_embedding.linear_2.weight")],
+                       h->pptr[h->pidx.at("time_embedding.linear_2.bias")], h->temb_act,
+                       (const float*)(h->packed + h->off_wcat), (const float*)(h->packed + h->off_bcat), h->temb_rows,
+                       h->temb_proj, st));
+        launches += 2;
+        break;
+      }
+      case OP_CONV_IN:
+        CK(launch_conv_in(x, h->pptr[h->pidx.at("conv_in.weight")], h->pptr[h->pidx.at("conv_in.bias")], h->N,
+                          c.in_channels, op.H, op.W, op.C, op.dst, op.conv.stats, st));
+        ++launches;
+        break;
+      case OP_GN:
+        CK(launch_gn_apply(op.gn, st));
+        ++launches;
+        break;
+      case OP_CONV:
+        CK(launch_conv_tc(op.conv, h->num_sms, st));
+        ++launches;
+        break;
+      case OP_UPSAMPLE:
+        CK(launch_upsample2x(op.src, op.dst, h->N, op.C, op.H, op.W, st));
+        ++launches;
+        break;
+      case OP_PARITY:
+        CK(launch_parity_split(op.src, op.dst, h->N, op.C, op.H, op.W, st));
+        ++launches;
+        break;
+      case OP_ATTN:
+        CK(launch_attention(op.src, op.dst, h->N, op.C, op.H, op.W, st));
+        ++launches;
+        break;
+      case OP_CONV_OUT: {
+        ConvOutParams p = op.co;
+        p.eps_out = eps_out;
+        p.x = x; p.z = z; p.x_out = x_out;
+        if (coef) {
+          p.coef.sqrt_1m_at = coef->sqrt_1m_at; p.coef.inv_sqrt_at = coef->inv_sqrt_at; p.coef.clip = coef->clip;
+          p.coef.c_x0 = coef->c_x0; p.coef.c_xt = coef->c_xt; p.coef.c_eps = coef->c_eps; p.coef.c_z = coef->c_z;
+          p.coef.do_clip = coef->do_clip;
+        }
+        CK(launch_conv_out(p, st));
+        ++launches;
+        break;
+      }
+    }
+  }
+  h->last_launches = launches;
+  return 0;
+}
+
+extern "C" int b200ad_unet_forward(b200ad_unet* h, const float* x, const float* t, float* eps_out, void* stream) {
+  return run_plan(h, x, t, nullptr, nullptr, nullptr, eps_out, (cudaStream_t)stream);
+}
+extern "C" int b200ad_unet_forward_step(b200ad_unet* h, const float* x, const float* t, const float* z,
+                                        const b200ad_step_coef* coef, float* x_out, float* eps_out, void* stream) {
+  if (!coef || !x_out) return set_err("coef and x_out are required");
+  return run_plan(h, x, t, z, coef, x_out, eps_out, (cudaStream_t)stream);
+}
+extern "C" int b200ad_unet_last_launch_count(const b200ad_unet* h) { return h->last_launches; }
+
+extern "C" int b200ad_unet_debug_tensor(b200ad_unet* h, const char* name, float* dst, int* dims, void* stream) {
+  auto it = h->taps.find(name);
+  if (it == h->taps.end()) return set_err("unknown tap '%s'", name);
+  const Act& a = it->second;
+  if (dims) { dims[0] = a.C; dims[1] = a.H; dims[2] = a.W; }
+  if (dst) CK(launch_pf8_to_nchw(a.p, dst, h->N, a.C, a.H, a.W, (cudaStream_t)stream));
+  return a.C;
+}

@@ -1,0 +1,241 @@
+"""`UNet2DModel` — drop-in for `diffusers.UNet2DModel` as the reference constructs and calls it
+(scripts/train_unet.py:115-137; audiodiffusion/pipeline_audio_diffusion.py:118-126,160-163,237).
+
+Same constructor kwargs, same state-dict key layout and the same call convention
+`unet(sample, timestep)["sample"]`; the forward runs entirely in libb200ad.so (tcgen05 implicit-GEMM
+convs, fused GroupNorm statistics, fused scheduler step).  PyTorch owns every tensor: parameters are
+ordinary fp32 `nn.Parameter`s, the packed bf16 weights and the activation workspace are torch byte tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional, Sequence, Tuple, Union
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import MAX_BLOCKS, StepCoefC, UNetConfigC
+
+
+class UNet2DOutput(dict):
+    """Indexable by ["sample"] and attribute `.sample`, like diffusers' BaseOutput."""
+
+    def __init__(self, sample):
+        super().__init__(sample=sample)
+        self.sample = sample
+
+
+class _Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+def _set_deep(root: nn.Module, dotted: str, p: nn.Parameter) -> None:
+    parts = dotted.split(".")
+    m = root
+    for name in parts[:-1]:
+        if name not in m._modules:
+            m.add_module(name, nn.Module())
+        m = m._modules[name]
+    m.register_parameter(parts[-1], p)
+
+
+class UNet2DModel(nn.Module):
+    def __init__(
+        self,
+        sample_size: Optional[Union[int, Tuple[int, int]]] = None,
+        in_channels: int = 3,
+        out_channels: int = 3,
+        center_input_sample: bool = False,
+        time_embedding_type: str = "positional",
+        freq_shift: int = 0,
+        flip_sin_to_cos: bool = True,
+        down_block_types: Sequence[str] = ("DownBlock2D", "AttnDownBlock2D", "AttnDownBlock2D", "AttnDownBlock2D"),
+        up_block_types: Sequence[str] = ("AttnUpBlock2D", "AttnUpBlock2D", "AttnUpBlock2D", "UpBlock2D"),
+        block_out_channels: Sequence[int] = (224, 448, 672, 896),
+        layers_per_block: int = 2,
+        mid_block_scale_factor: float = 1,
+        downsample_padding: int = 1,
+        act_fn: str = "silu",
+        attention_head_dim: Optional[int] = 8,
+        norm_num_groups: int = 32,
+        norm_eps: float = 1e-5,
+        resnet_time_scale_shift: str = "default",
+        add_attention: bool = True,
+        seed: Optional[int] = None,
+    ):
+        super().__init__()
+        unsupported = []
+        if center_input_sample: unsupported.append("center_input_sample")
+        if time_embedding_type != "positional": unsupported.append("time_embedding_type")
+        if freq_shift != 0 or not flip_sin_to_cos: unsupported.append("freq_shift/flip_sin_to_cos")
+        if mid_block_scale_factor != 1 or downsample_padding != 1: unsupported.append("scale/padding")
+        if act_fn != "silu" or resnet_time_scale_shift != "default" or not add_attention: unsupported.append("act/shift/attn")
+        if len(block_out_channels) > MAX_BLOCKS: unsupported.append("too many blocks")
+        for t in down_block_types:
+            if t not in ("DownBlock2D", "AttnDownBlock2D"): unsupported.append(t)
+        for t in up_block_types:
+            if t not in ("UpBlock2D", "AttnUpBlock2D"): unsupported.append(t)
+        if unsupported:
+            raise ValueError(f"UNet2DModel(b200): unsupported configuration: {unsupported}")
+        self.sample_size = sample_size
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.config = _Cfg(
+            sample_size=sample_size, in_channels=in_channels, out_channels=out_channels,
+            down_block_types=tuple(down_block_types), up_block_types=tuple(up_block_types),
+            block_out_channels=tuple(block_out_channels), layers_per_block=layers_per_block,
+            attention_head_dim=attention_head_dim, norm_num_groups=norm_num_groups, norm_eps=norm_eps,
+            center_input_sample=center_input_sample, time_embedding_type=time_embedding_type, freq_shift=freq_shift,
+            flip_sin_to_cos=flip_sin_to_cos, mid_block_scale_factor=mid_block_scale_factor,
+            downsample_padding=downsample_padding, act_fn=act_fn, resnet_time_scale_shift=resnet_time_scale_shift,
+            add_attention=add_attention, _class_name="UNet2DModel")
+
+        c = UNetConfigC()
+        c.in_channels, c.out_channels = in_channels, out_channels
+        c.layers_per_block, c.num_blocks = layers_per_block, len(block_out_channels)
+        for i, v in enumerate(block_out_channels):
+            c.block_out_channels[i] = int(v)
+            c.down_attn[i] = 1 if down_block_types[i] == "AttnDownBlock2D" else 0
+            c.up_attn[i] = 1 if up_block_types[i] == "AttnUpBlock2D" else 0
+        c.norm_num_groups, c.norm_eps = norm_num_groups, norm_eps
+        c.attention_head_dim = attention_head_dim if attention_head_dim is not None else -1
+        self._c = c
+        L = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(L.b200ad_unet_create(C.byref(c), C.byref(h)))
+        self._h = h
+        # parameter table comes from the library (diffusers naming); PyTorch default init
+        g = torch.Generator().manual_seed(seed) if seed is not None else None
+        self._pnames = []
+        dims = (C.c_int64 * 4)()
+        shapes: Dict[str, Tuple[int, ...]] = {}
+        for i in range(L.b200ad_unet_num_params(h)):
+            name = L.b200ad_unet_param_name(h, i).decode()
+            nd = L.b200ad_unet_param_shape(h, i, dims)
+            shapes[name] = tuple(int(dims[k]) for k in range(nd))
+            self._pnames.append(name)
+        for name in self._pnames:
+            shape = shapes[name]
+            is_norm = (".norm" in name) or ("group_norm" in name) or name.startswith("conv_norm_out")
+            if is_norm:
+                t = torch.ones(shape) if name.endswith(".weight") else torch.zeros(shape)
+            else:
+                wshape = shapes[name[: name.rfind(".")] + ".weight"]
+                bound = 1.0 / math.sqrt(int(math.prod(wshape[1:])))
+                t = (torch.rand(shape, generator=g) * 2 - 1) * bound
+            _set_deep(self, name, nn.Parameter(t))
+        self._packed = None
+        self._packed_key = None
+        self._ws = None
+        self._ws_key = None
+
+    # ------------------------------------------------------------------ engine plumbing
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.lib().b200ad_unet_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _named(self) -> Dict[str, nn.Parameter]:
+        return dict(self.named_parameters())
+
+    @property
+    def device(self) -> torch.device:
+        return next(self.parameters()).device
+
+    def _ensure_bound(self, n: int, hh: int, ww: int) -> None:
+        _lib.require_cuda()
+        L = _lib.lib()
+        named = self._named()
+        params = [named[k] for k in self._pnames]
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise _lib.B200ADError("UNet2DModel(b200): parameters must live on a CUDA device (call .to('cuda'))")
+        for p in params:
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise _lib.B200ADError("UNet2DModel(b200): parameters must be contiguous fp32 (master weights)")
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is None or self._packed.device != dev:
+            self._packed = torch.empty(L.b200ad_unet_packed_bytes(self._h), dtype=torch.uint8, device=dev)
+            self._packed_key = None
+            self._ws_key = None
+        if key != self._packed_key:
+            arr = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
+            _lib.check(L.b200ad_unet_set_params(self._h, arr, self._packed.data_ptr(), self._packed.numel(),
+                                                _lib.stream_ptr()))
+            self._packed_key = key
+            self._ws_key = None  # plan holds parameter pointers
+        wkey = (n, hh, ww, dev)
+        if wkey != self._ws_key:
+            need = L.b200ad_unet_workspace_bytes(self._h, n, hh, ww)
+            if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+                self._ws = None
+                self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            _lib.check(L.b200ad_unet_bind_workspace(self._h, self._ws.data_ptr(), self._ws.numel(), n, hh, ww,
+                                                    _lib.stream_ptr()))
+            self._ws_key = wkey
+
+    def _timesteps(self, timestep, n: int, dev) -> torch.Tensor:
+        t = timestep
+        if not torch.is_tensor(t):
+            t = torch.tensor([t], dtype=torch.float32, device=dev)
+        t = t.to(device=dev, dtype=torch.float32).reshape(-1)
+        if t.numel() == 1:
+            t = t.expand(n)
+        if t.numel() != n:
+            raise ValueError("timestep must be a scalar or have one entry per sample")
+        return t.contiguous()
+
+    # ------------------------------------------------------------------ public call
+    def forward(self, sample: torch.Tensor, timestep, return_dict: bool = True):
+        """ε = unet(sample, timestep)["sample"] — pipeline_audio_diffusion.py:163."""
+        if sample.requires_grad or (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+                                    and self.training):
+            raise NotImplementedError("UNet2DModel(b200): the backward pass is not built yet (inference only)")
+        x = sample.to(torch.float32).contiguous()
+        n, _, hh, ww = x.shape
+        with torch.cuda.device(x.device):
+            self._ensure_bound(n, hh, ww)
+            t = self._timesteps(timestep, n, x.device)
+            out = torch.empty((n, self.out_channels, hh, ww), dtype=torch.float32, device=x.device)
+            _lib.check(_lib.lib().b200ad_unet_forward(self._h, x.data_ptr(), t.data_ptr(), out.data_ptr(),
+                                                      _lib.stream_ptr()))
+        if not return_dict:
+            return (out,)
+        return UNet2DOutput(out)
+
+    @torch.no_grad()
+    def forward_step(self, sample: torch.Tensor, timestep, coef: StepCoefC, noise: Optional[torch.Tensor] = None,
+                     out: Optional[torch.Tensor] = None, want_eps: bool = False):
+        """Fused `scheduler.step(unet(sample, t), t, sample)["prev_sample"]` (pipeline_audio_diffusion.py:163-179)."""
+        x = sample.to(torch.float32).contiguous()
+        n, _, hh, ww = x.shape
+        with torch.cuda.device(x.device):
+            self._ensure_bound(n, hh, ww)
+            t = self._timesteps(timestep, n, x.device)
+            if out is None:
+                out = torch.empty_like(x)
+            eps = torch.empty_like(x) if want_eps else None
+            z = noise.to(torch.float32).contiguous() if noise is not None else None
+            _lib.check(_lib.lib().b200ad_unet_forward_step(
+                self._h, x.data_ptr(), t.data_ptr(), z.data_ptr() if z is not None else None, C.byref(coef),
+                out.data_ptr(), eps.data_ptr() if eps is not None else None, _lib.stream_ptr()))
+        return (out, eps) if want_eps else out
+
+    def debug_tensor(self, name: str) -> torch.Tensor:
+        """fp32 NCHW copy of a named internal activation of the last forward (parity tests)."""
+        L = _lib.lib()
+        dims = (C.c_int * 3)()
+        _lib.check(min(0, L.b200ad_unet_debug_tensor(self._h, name.encode(), None, dims, _lib.stream_ptr())))
+        n = self._ws_key[0]
+        out = torch.empty((n, dims[0], dims[1], dims[2]), dtype=torch.float32, device=self.device)
+        _lib.check(min(0, L.b200ad_unet_debug_tensor(self._h, name.encode(), out.data_ptr(), dims, _lib.stream_ptr())))
+        return out
+
+    @property
+    def last_launch_count(self) -> int:
+        return _lib.lib().b200ad_unet_last_launch_count(self._h)

@@ -1,0 +1,119 @@
+/* libb200ad — C ABI of the B200-native audio-diffusion hot path.
+ *
+ * The reference (teticio/audio-diffusion) has no FFI: its boundary is Python duck-typing on the objects that
+ * `AudioDiffusionPipeline.__call__` drives (audiodiffusion/pipeline_audio_diffusion.py:71-205) and on
+ * `Mel` (audiodiffusion/mel.py:44-168).  Every entry point below names the reference call it replaces.
+ *
+ * Conventions: plain pointers and sizes; all tensor pointers are DEVICE pointers owned by the caller
+ * (PyTorch); `stream` is a cudaStream_t passed as void*; kernels are enqueued and never synchronise;
+ * return value 0 = ok, negative = error (message via b200ad_last_error()).  Handles are per device and
+ * not thread-safe (the reference is single-threaded synchronous Python; one process per GPU).
+ */
+#ifndef B200AD_H
+#define B200AD_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200AD_MAX_BLOCKS 8
+
+const char* b200ad_last_error(void);
+int b200ad_version(void);
+
+/* ---- U-Net: replaces diffusers.UNet2DModel as constructed at scripts/train_unet.py:115-137 ------------ */
+typedef struct {
+  int in_channels, out_channels;      /* 1 / 1 (or vqvae latent_channels), train_unet.py:117-118        */
+  int layers_per_block;               /* 2                                                               */
+  int num_blocks;                     /* len(block_out_channels)                                         */
+  int block_out_channels[B200AD_MAX_BLOCKS];
+  int down_attn[B200AD_MAX_BLOCKS];   /* 1 where down_block_types[i] == "AttnDownBlock2D"                */
+  int up_attn[B200AD_MAX_BLOCKS];     /* 1 where up_block_types[i] == "AttnUpBlock2D"                    */
+  int norm_num_groups;                /* 32                                                              */
+  float norm_eps;                     /* 1e-5                                                            */
+  int attention_head_dim;             /* 8 (only 8 is implemented)                                       */
+} b200ad_unet_config;
+
+typedef struct b200ad_unet b200ad_unet;
+
+int b200ad_unet_create(const b200ad_unet_config* cfg, b200ad_unet** out);
+void b200ad_unet_destroy(b200ad_unet* h);
+
+/* Parameter table in diffusers state-dict naming, so hub checkpoints bind unchanged. */
+int b200ad_unet_num_params(const b200ad_unet* h);
+const char* b200ad_unet_param_name(const b200ad_unet* h, int i);
+/* writes up to 4 dims, returns ndim */
+int b200ad_unet_param_shape(const b200ad_unet* h, int i, int64_t* dims);
+
+/* Device bytes for the bf16-packed weights, and for activations at a given batch / resolution. */
+size_t b200ad_unet_packed_bytes(const b200ad_unet* h);
+size_t b200ad_unet_workspace_bytes(const b200ad_unet* h, int N, int H, int W);
+
+/* Bind fp32 parameters (device pointers, in table order) and pack them for the tensor-core kernels into
+ * `packed` (caller-owned device buffer of b200ad_unet_packed_bytes()).  Call again after weights change. */
+int b200ad_unet_set_params(b200ad_unet* h, const float* const* params, void* packed, size_t packed_bytes, void* stream);
+
+/* Bind (and zero) the activation workspace for batch N at H x W and build the launch plan. */
+int b200ad_unet_bind_workspace(b200ad_unet* h, void* workspace, size_t bytes, int N, int H, int W, void* stream);
+
+/* model_output = unet(sample, timestep)["sample"]   (pipeline_audio_diffusion.py:163, :237).
+ * x, eps_out: fp32 NCHW [N, in/out_channels, H, W]; t: float[N] timesteps (device). */
+int b200ad_unet_forward(b200ad_unet* h, const float* x, const float* t, float* eps_out, void* stream);
+
+/* Scheduler-update coefficients (host scalars, computed exactly as DDPMScheduler.step / DDIMScheduler.step do,
+ * pipeline_audio_diffusion.py:165-179):
+ *   x0  = clamp((x - sqrt_1m_at * eps) * inv_sqrt_at, -clip, +clip)   (clamp only if do_clip)
+ *   out = c_x0 * x0 + c_xt * x + c_eps * eps + c_z * z */
+typedef struct {
+  float sqrt_1m_at, inv_sqrt_at, clip, c_x0, c_xt, c_eps, c_z;
+  int do_clip;
+} b200ad_step_coef;
+
+/* One denoising step with the scheduler update fused into the U-Net output kernel:
+ * x_out = scheduler.step(unet(x, t), t, x)["prev_sample"].  z may be NULL (t == 0 / DDIM eta == 0);
+ * eps_out may be NULL; x_out may alias x. */
+int b200ad_unet_forward_step(b200ad_unet* h, const float* x, const float* t, const float* z,
+                             const b200ad_step_coef* coef, float* x_out, float* eps_out, void* stream);
+
+/* Debug / parity: copy a named internal activation of the last forward to fp32 NCHW.
+ * Names follow the oracle taps (e.g. "conv_in", "down_blocks.0.resnets.0", "mid_block.attentions.0").
+ * Returns the number of channels, or negative. dst may be NULL to query (dims[0..2] = C, H, W). */
+int b200ad_unet_debug_tensor(b200ad_unet* h, const char* name, float* dst, int* dims, void* stream);
+
+/* Number of kernel launches the last forward enqueued. */
+int b200ad_unet_last_launch_count(const b200ad_unet* h);
+
+/* ---- Op-level entry points (parity tests call the kernels in isolation) ------------------------------- */
+/* conv2d (KHxKW in {1x1, 3x3}, stride 1 or 2, padding KH/2) on fp32 NCHW tensors through the tcgen05
+ * implicit-GEMM kernel; optional residual (fp32 NCHW, cout channels) and per-sample additive vector
+ * temb [N][cout]; stats_out (optional) receives [N][cout/4][2] (sum, sumsq). scratch >= b200ad_conv2d_scratch_bytes. */
+size_t b200ad_conv2d_scratch_bytes(int N, int cin, int cout, int H, int W, int K, int stride);
+int b200ad_conv2d(const float* x, const float* w, const float* bias, const float* temb, const float* residual,
+                  float* y, float* stats_out, int N, int cin, int cout, int H, int W, int K, int stride,
+                  void* scratch, size_t scratch_bytes, void* stream);
+/* GroupNorm(groups, eps) [+ SiLU] on fp32 NCHW through the stats + apply kernels. */
+int b200ad_group_norm(const float* x, const float* gamma, const float* beta, float* y, int N, int C, int H, int W,
+                      int groups, float eps, int silu, void* scratch, size_t scratch_bytes, void* stream);
+
+/* ---- Mel codec: replaces Mel.audio_slice_to_image / Mel.image_to_audio (audiodiffusion/mel.py:135-168) -- */
+typedef struct {
+  int x_res, y_res, sample_rate, n_fft, hop_length, top_db, n_iter;
+} b200ad_mel_config;
+size_t b200ad_mel_scratch_bytes(const b200ad_mel_config* cfg, int n);
+/* audio [n][x_res*hop_length - 1] fp32 (device) -> uint8 images [n][y_res][x_res] (device). mel.py:145-149 */
+int b200ad_mel_encode(const b200ad_mel_config* cfg, const float* audio, uint8_t* images, int n,
+                      void* scratch, size_t scratch_bytes, void* stream);
+/* uint8 images [n][y_res][x_res] -> audio [n][(x_res-1)*hop_length] fp32. mel.py:162-167.
+ * phase_seed seeds the Griffin-Lim random phase (the reference leaves it unseeded). */
+int b200ad_mel_decode(const b200ad_mel_config* cfg, const uint8_t* images, float* audio, int n, uint64_t phase_seed,
+                      void* scratch, size_t scratch_bytes, void* stream);
+
+/* float sample -> uint8 image, pipeline_audio_diffusion.py:192-194: round-half-even((x/2+.5).clamp(0,1)*255). */
+int b200ad_sample_to_u8(const float* x, uint8_t* img, size_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200AD_H */

@@ -1,0 +1,117 @@
+"""GPU parity of single kernels (through the C ABI) against plain PyTorch fp32 on the CPU.
+
+Tolerances: operands are rounded to bf16 on both sides, accumulation is fp32, the kernel stores bf16
+(relative rounding 2^-9), so |err| <= 1.5e-2 * max|ref| is the stated per-op bound.
+"""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def _conv(cuda, N, cin, cout, H, W, K, stride, temb=False, res=False, seed=0):
+    from audio_diffusion_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(seed)
+    x = _bf(torch.randn(N, cin, H, W, generator=g))
+    w = _bf(torch.randn(cout, cin, K, K, generator=g) / (cin * K * K) ** 0.5)
+    b = torch.randn(cout, generator=g)
+    te = torch.randn(N, cout, generator=g) if temb else None
+    Ho, Wo = H // stride, W // stride
+    r = _bf(torch.randn(N, cout, Ho, Wo, generator=g)) if res else None
+    ref = F.conv2d(x, w, b, stride=stride, padding=K // 2)
+    if temb:
+        ref = ref + te[:, :, None, None]
+    if res:
+        ref = ref + r
+    d = lambda t: t.to(cuda).contiguous() if t is not None else None
+    xd, wd, bd, ted, rd = d(x), d(w), d(b), d(te), d(r)
+    y = torch.empty(N, cout, Ho, Wo, device=cuda)
+    stats = torch.empty(N, cout // 4, 2, device=cuda)
+    nb = L.b200ad_conv2d_scratch_bytes(N, cin, cout, H, W, K, stride)
+    scratch = torch.empty(nb, dtype=torch.uint8, device=cuda)
+    p = lambda t: t.data_ptr() if t is not None else None
+    _lib.check(L.b200ad_conv2d(p(xd), p(wd), p(bd), p(ted), p(rd), p(y), p(stats), N, cin, cout, H, W, K, stride,
+                               p(scratch), nb, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    y = y.cpu()
+    err = (y - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 1.5e-2 * scale, f"conv err {err} vs scale {scale}"
+    # GroupNorm partial statistics of the stored output, per (sample, 4-channel quad)
+    q = ref.view(N, cout // 4, 4, Ho * Wo)
+    s_ref = torch.stack([q.sum(dim=(2, 3)), (q * q).sum(dim=(2, 3))], dim=-1)
+    s = stats.cpu()
+    tol = 2e-2 * s_ref[..., 1].abs().max().item()
+    assert (s - s_ref).abs().max().item() <= tol + 1e-3 * Ho * Wo
+
+
+@pytest.mark.parametrize("H,W", [(32, 32), (16, 16), (8, 8), (64, 64)])
+def test_conv3x3_flat(cuda, H, W):
+    _conv(cuda, 2, 128, 128, H, W, 3, 1)
+
+
+def test_conv3x3_wide(cuda):
+    _conv(cuda, 2, 128, 128, 8, 128, 3, 1)
+    _conv(cuda, 1, 64, 128, 12, 256, 3, 1, seed=3)
+
+
+def test_conv3x3_channels(cuda):
+    _conv(cuda, 1, 384, 256, 16, 16, 3, 1, temb=True, res=True)
+
+
+def test_conv1x1(cuda):
+    _conv(cuda, 2, 256, 128, 16, 16, 1, 1, res=True)
+    _conv(cuda, 1, 128, 384, 4, 128, 1, 1)
+
+
+def test_conv3x3_stride2(cuda):
+    _conv(cuda, 2, 128, 128, 32, 32, 3, 2)
+    _conv(cuda, 1, 128, 128, 16, 256, 3, 2, seed=5)
+
+
+@pytest.mark.parametrize("silu", [0, 1])
+def test_group_norm(cuda, silu):
+    from audio_diffusion_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(1)
+    N, Cc, H, W = 2, 384, 16, 16
+    x = _bf(torch.randn(N, Cc, H, W, generator=g) * 2 + 0.5)
+    gamma = torch.randn(Cc, generator=g)
+    beta = torch.randn(Cc, generator=g)
+    ref = F.group_norm(x, 32, gamma, beta, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    xd, gd, bd = x.to(cuda), gamma.to(cuda), beta.to(cuda)
+    y = torch.empty_like(xd)
+    nb = 1 << 26
+    scratch = torch.empty(nb, dtype=torch.uint8, device=cuda)
+    _lib.check(L.b200ad_group_norm(xd.data_ptr(), gd.data_ptr(), bd.data_ptr(), y.data_ptr(), N, Cc, H, W, 32, 1e-5,
+                                   silu, scratch.data_ptr(), nb, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    err = (y.cpu() - ref).abs().max().item()
+    assert err <= 1.5e-2 * ref.abs().max().item(), err
+
+
+def test_sample_to_u8_bit_exact(cuda):
+    """pipeline_audio_diffusion.py:192-194 integer boundary — bit-exact vs numpy."""
+    from audio_diffusion_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(1 << 16, generator=g) * 1.2
+    # include exact .5 ties: (k + 0.5) / 255 * 2 - 1
+    ties = ((torch.arange(0, 255, dtype=torch.float32) + 0.5) / 255.0) * 2 - 1
+    x = torch.cat([x, ties])
+    ref = ((x / 2 + 0.5).clamp(0, 1).numpy() * 255).round().astype("uint8")
+    xd = x.to(cuda)
+    out = torch.empty(x.numel(), dtype=torch.uint8, device=cuda)
+    _lib.check(L.b200ad_sample_to_u8(xd.data_ptr(), out.data_ptr(), x.numel(), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert (out.cpu().numpy() == ref).all()

@@ -1,0 +1,110 @@
+"""GPU parity of the whole U-Net forward (C ABI `b200ad_unet_forward`) against the CPU oracle.
+
+Tolerance (stated): the CUDA path keeps activations and GEMM operands in bf16 with fp32 accumulation and
+fp32 GroupNorm statistics; the oracle is fp32 end to end.  Per layer and for the final epsilon we require
+max|err| <= 6% of the oracle tensor's max-abs and rms error <= 1.5% of its rms.
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(
+    in_channels=1, out_channels=1, layers_per_block=2, block_out_channels=(128, 256),
+    down_block_types=("DownBlock2D", "AttnDownBlock2D"), up_block_types=("AttnUpBlock2D", "UpBlock2D"))
+
+
+def _build(cuda, cfg_kwargs, sample_size, seed=0):
+    from audio_diffusion_b200.unet import UNet2DModel
+    from oracle.unet_oracle import UNetConfig, init_weights
+    ocfg = UNetConfig(sample_size=sample_size, **cfg_kwargs)
+    w = init_weights(ocfg, seed=seed)
+    model = UNet2DModel(sample_size=sample_size, **cfg_kwargs)
+    sd = model.state_dict()
+    assert set(sd.keys()) == set(w.keys())
+    model.load_state_dict(w)
+    return model.to(cuda), ocfg, w
+
+
+def _cmp(name, got, ref, max_tol=6e-2, rms_tol=1.5e-2):
+    err = (got - ref)
+    mx = err.abs().max().item() / (ref.abs().max().item() + 1e-12)
+    rms = (err.pow(2).mean().sqrt() / (ref.pow(2).mean().sqrt() + 1e-12)).item()
+    assert mx <= max_tol and rms <= rms_tol, f"{name}: max-rel {mx:.4f} rms-rel {rms:.4f}"
+    return mx, rms
+
+
+def test_unet_small_layers(cuda):
+    from oracle.unet_oracle import unet_forward
+    os.environ["B200AD_DEBUG_NOPOOL"] = "1"
+    try:
+        model, ocfg, w = _build(cuda, SMALL, (32, 32))
+        g = torch.Generator().manual_seed(42)
+        x = torch.randn(2, 1, 32, 32, generator=g)
+        t = torch.tensor([17, 801])
+        taps = {}
+        ref = unet_forward(w, ocfg, x, t, taps)
+        with torch.no_grad():
+            out = model(x.to(cuda), t.to(cuda))["sample"]
+        torch.cuda.synchronize()
+        report = []
+        for name in ["conv_in", "down_blocks.0.resnets.0.h1", "down_blocks.0.resnets.0", "down_blocks.0.resnets.1",
+                     "down_blocks.0.downsamplers.0.conv", "down_blocks.1.resnets.0", "down_blocks.1.attentions.0",
+                     "down_blocks.1.attentions.1", "mid_block.resnets.0", "mid_block.attentions.0",
+                     "mid_block.resnets.1", "up_blocks.0.resnets.0", "up_blocks.0.attentions.2",
+                     "up_blocks.0.upsamplers.0.conv", "up_blocks.1.resnets.0", "up_blocks.1.resnets.2"]:
+            got = model.debug_tensor(name).cpu()
+            report.append((name,) + _cmp(name, got, taps[name]))
+        _cmp("eps", out.cpu(), ref)
+        for r in report:
+            print("%-40s max-rel %.4f rms-rel %.4f" % r)
+    finally:
+        os.environ.pop("B200AD_DEBUG_NOPOOL", None)
+
+
+def test_unet_small_pooled_matches(cuda):
+    """Buffer pooling must not change results; scalar timestep broadcast (pipeline_audio_diffusion.py:163)."""
+    from oracle.unet_oracle import unet_forward
+    model, ocfg, w = _build(cuda, SMALL, (32, 32), seed=1)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(3, 1, 32, 32, generator=g)
+    ref = unet_forward(w, ocfg, x, torch.tensor(999))
+    with torch.no_grad():
+        out1 = model(x.to(cuda), torch.tensor(999))["sample"].cpu()
+        out2 = model(x.to(cuda), 999)["sample"].cpu()
+    _cmp("eps", out1, ref)
+    assert torch.equal(out1, out2) or (out1 - out2).abs().max() < 1e-3 * ref.abs().max()
+    assert model.last_launch_count > 0
+
+
+def test_unet_reference_arch_64(cuda):
+    """The exact architecture of scripts/train_unet.py:115-137 at 64x64 (config C1 shape), batch 1."""
+    from oracle.unet_oracle import unet_forward
+    ref_arch = dict(
+        in_channels=1, out_channels=1, layers_per_block=2, block_out_channels=(128, 128, 256, 256, 512, 512),
+        down_block_types=("DownBlock2D",) * 4 + ("AttnDownBlock2D", "DownBlock2D"),
+        up_block_types=("UpBlock2D", "AttnUpBlock2D", "UpBlock2D", "UpBlock2D", "UpBlock2D", "UpBlock2D"))
+    model, ocfg, w = _build(cuda, ref_arch, (64, 64))
+    assert sum(p.numel() for p in model.parameters()) == 113_668_609
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(1, 1, 64, 64, generator=g)
+    ref = unet_forward(w, ocfg, x, torch.tensor(500))
+    with torch.no_grad():
+        out = model(x.to(cuda), 500)["sample"].cpu()
+    _cmp("eps", out, ref)
+
+
+def test_unet_wide_mode_256(cuda):
+    """256-wide images take the 'wide' tiling of the conv kernel (4 rows x 128 px)."""
+    from oracle.unet_oracle import unet_forward
+    cfg = dict(in_channels=1, out_channels=1, layers_per_block=1, block_out_channels=(128, 128),
+               down_block_types=("DownBlock2D", "DownBlock2D"), up_block_types=("UpBlock2D", "UpBlock2D"))
+    model, ocfg, w = _build(cuda, cfg, (16, 256))
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 1, 16, 256, generator=g)
+    ref = unet_forward(w, ocfg, x, torch.tensor(10))
+    with torch.no_grad():
+        out = model(x.to(cuda), 10)["sample"].cpu()
+    _cmp("eps", out, ref)
