@@ -49,14 +49,16 @@ SYMBOLS = {
     "b200ad_unet_bind_workspace": (_I, [_VP, _VP, _SZ, _I, _I, _I, _VP]),
     "b200ad_unet_forward": (_I, [_VP, _VP, _VP, _VP, _VP]),
     "b200ad_unet_forward_step": (_I, [_VP, _VP, _VP, _VP, C.POINTER(StepCoefC), _VP, _VP, _VP]),
+    "b200ad_unet_profile_step": (_I, [_VP, _VP, _VP, _VP, C.POINTER(StepCoefC), _VP, C.POINTER(C.c_float),
+                                      C.POINTER(_I), C.POINTER(C.c_double), _I, _VP]),
     "b200ad_unet_debug_tensor": (_I, [_VP, C.c_char_p, _VP, C.POINTER(_I), _VP]),
     "b200ad_unet_last_launch_count": (_I, [_VP]),
     "b200ad_conv2d_scratch_bytes": (_SZ, [_I] * 7),
     "b200ad_conv2d": (_I, [_VP] * 7 + [_I] * 7 + [_VP, _SZ, _VP]),
     "b200ad_group_norm": (_I, [_VP] * 4 + [_I] * 5 + [C.c_float, _I, _VP, _SZ, _VP]),
     "b200ad_mel_scratch_bytes": (_SZ, [C.POINTER(MelConfigC), _I]),
-    "b200ad_mel_encode": (_I, [C.POINTER(MelConfigC), _VP, _VP, _I, _VP, _SZ, _VP]),
-    "b200ad_mel_decode": (_I, [C.POINTER(MelConfigC), _VP, _VP, _I, C.c_uint64, _VP, _SZ, _VP]),
+    "b200ad_mel_encode": (_I, [C.POINTER(MelConfigC), _VP, _VP, _VP, _I, _VP, _SZ, _VP]),
+    "b200ad_mel_decode": (_I, [C.POINTER(MelConfigC), _VP, _VP, _VP, _I, C.c_uint64, _VP, _SZ, _VP]),
     "b200ad_sample_to_u8": (_I, [_VP, _VP, _SZ, _VP]),
 }
 

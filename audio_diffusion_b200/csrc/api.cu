@@ -33,7 +33,7 @@ static ConvScratch conv_scratch_layout(int N, int cin, int cout, int H, int W, i
   s.res = off; off = al(off + (size_t)N * (cout / 8) * go.PL * 16);
   s.out = off; off = al(off + (size_t)N * (cout / 8) * go.PL * 16);
   s.wpack = off; off = al(off + (size_t)(cout / 128) * (cin / 16) * K * K * CONV_B_TAP);
-  s.stats = off; off = al(off + (size_t)N * (cout / 4) * 2 * 4);
+  s.stats = off; off = al(off + (size_t)N * (cout / 4) * 2 * sizeof(stat_t));
   s.total = off;
   return s;
 }
@@ -60,7 +60,7 @@ extern "C" int b200ad_conv2d(const float* x, const float* w, const float* bias, 
   __nv_bfloat16* rp = (__nv_bfloat16*)(sb + L.res);
   __nv_bfloat16* op = (__nv_bfloat16*)(sb + L.out);
   __nv_bfloat16* wp = (__nv_bfloat16*)(sb + L.wpack);
-  float* stp = (float*)(sb + L.stats);
+  stat_t* stp = (stat_t*)(sb + L.stats);
   CK(launch_nchw_to_pf8(x, xp, N, cin, H, W, st));
   if (residual) CK(launch_nchw_to_pf8(residual, rp, N, cout, Ho, Wo, st));
 
@@ -110,7 +110,7 @@ extern "C" int b200ad_conv2d(const float* x, const float* w, const float* bias, 
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   CK(launch_conv_tc(p, sms, st));
   CK(launch_pf8_to_nchw(op, y, N, cout, Ho, Wo, st));
-  if (stats_out) CK(cudaMemcpyAsync(stats_out, stp, (size_t)N * (cout / 4) * 2 * 4, cudaMemcpyDeviceToDevice, st));
+  if (stats_out) CK(launch_stats_to_float(stp, stats_out, N * (cout / 4) * 2, st));
   return 0;
 }
 
@@ -119,14 +119,14 @@ extern "C" int b200ad_group_norm(const float* x, const float* gamma, const float
   if (C % 32) return set_err("group_norm: C %% 32 != 0");
   const Geom g = make_geom(N, H, W);
   const size_t tb = al((size_t)N * (C / 8) * g.PL * 16);
-  const size_t need = 2 * tb + al((size_t)N * (C / 4) * 8);
+  const size_t need = 2 * tb + al((size_t)N * (C / 4) * 2 * sizeof(stat_t));
   if (scratch_bytes < need) return set_err("group_norm: scratch too small (%zu < %zu)", scratch_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* sb = (uint8_t*)scratch;
   CK(cudaMemsetAsync(sb, 0, need, st));
   __nv_bfloat16* xp = (__nv_bfloat16*)sb;
   __nv_bfloat16* yp = (__nv_bfloat16*)(sb + tb);
-  float* stats = (float*)(sb + 2 * tb);
+  stat_t* stats = (stat_t*)(sb + 2 * tb);
   CK(launch_nchw_to_pf8(x, xp, N, C, H, W, st));
   CK(launch_quad_stats(xp, stats, N, C, H, W, st));
   GnApplyParams p{};

@@ -18,6 +18,9 @@ namespace b200ad {
 // Because pads and guards are real zeros, a 3x3 tap (dh, dw) of output pixel m is simply input
 // pixel m + dh*Wp + dw of the same flat sequence: every tap is a *shifted view* of one strip.
 // ----------------------------------------------------------------------------------------------
+// GroupNorm partial statistics are accumulated in fp64 so that the atomic order cannot change results.
+typedef double stat_t;
+
 struct Geom {
   int N, H, W, Wp, lead, PL;
 };

@@ -12,6 +12,8 @@
 // Accumulators: up to 4 pixel tiles x 128 fp32 columns = the whole TMEM, so one weight stage feeds 4 tiles.
 // Warp roles: warp 0 bulk-copy producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue
 //   (bias + timestep-embedding + residual, GroupNorm partial statistics for the consumer, bf16 store).
+#include <cstdlib>
+
 #include "conv_tc.cuh"
 
 namespace b200ad {
@@ -50,6 +52,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
   uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);           // full[3], empty[3], tmem_full, tmem_empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + 64);
   float* sbias = reinterpret_cast<float*>(ctrl + 128);          // 128 floats
+  uint2* mtab = reinterpret_cast<uint2*>(ctrl + 640);           // 36 (tile, tap) descriptor-offset entries
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = smem_u32(bars + CONV_STAGES);
@@ -72,84 +75,108 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================================ producer: bulk copies of A strips and B weight blocks
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-        const WorkItem wi = decode_work(p, w);
-        for (int s = 0; s < p.nseg; ++s) {
-          const ConvSeg& sg = p.seg[s];
-          const __nv_bfloat16* img = sg.src + (long long)wi.n * sg.img_stride;
-          const int nwin = p.wide ? (wi.G + sg.ht + sg.hb) : 1;
-          const int npix = p.wide ? (CONV_TM + sg.hl + sg.hr)
-                                  : (wi.G * CONV_TM + (sg.ht + sg.hb) * p.Wp + sg.hl + sg.hr);
-          const uint32_t a_bytes = (uint32_t)nwin * 2u * (uint32_t)npix * 16u;
-          const uint32_t b_bytes = (uint32_t)sg.ntaps * CONV_B_TAP;
-          for (int ks = 0; ks < sg.ksteps; ++ks) {
+    // ================================ producer: bulk copies of A strips and B weight blocks.
+    // Lane 0 owns the barrier protocol; lanes 0..2*nwin-1 each issue one A copy, lane 31 the B copy.
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      const WorkItem wi = decode_work(p, w);
+      for (int s = 0; s < p.nseg; ++s) {
+        const ConvSeg& sg = p.seg[s];
+        const int nwin = p.wide ? (wi.G + sg.ht + sg.hb) : 1;
+        const int npix = p.wide ? (CONV_TM + sg.hl + sg.hr)
+                                : (wi.G * CONV_TM + (sg.ht + sg.hb) * p.Wp + sg.hl + sg.hr);
+        const uint32_t row_bytes = (uint32_t)npix * 16u;
+        const uint32_t b_bytes = (uint32_t)sg.ntaps * CONV_B_TAP;
+        const uint32_t tx_bytes = (uint32_t)nwin * 2u * row_bytes + b_bytes;
+        // this lane's copy: source at k-step 0 and byte advance per k-step
+        const char* src = nullptr;
+        long long src_step = 0;
+        uint32_t dst_off = 0, bytes = 0;
+        if (lane < 2 * nwin) {
+          const int r = lane >> 1, pl = lane & 1;
+          const int pix0 = p.lead + wi.m0 + (r - sg.ht) * p.Wp - sg.hl;
+          src = reinterpret_cast<const char*>(sg.src + (long long)wi.n * sg.img_stride + ((long long)pl * p.PL + pix0) * 8);
+          src_step = (long long)2 * p.PL * 16;
+          dst_off = (uint32_t)lane * row_bytes;
+          bytes = row_bytes;
+        } else if (lane == 31) {
+          src = reinterpret_cast<const char*>(sg.wpack + (long long)wi.ntile * sg.ksteps * sg.ntaps * (CONV_B_TAP / 2));
+          src_step = (long long)b_bytes;
+          dst_off = CONV_A_STAGE;
+          bytes = b_bytes;
+        }
+        for (int ks = 0; ks < sg.ksteps; ++ks) {
+          const uint32_t full = bar_full + 8 * stage;
+          if (lane == 0) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            const uint32_t full = bar_full + 8 * stage;
-            mbar_arrive_expect_tx(full, a_bytes + b_bytes);
-            const uint32_t a_dst = smem_base + stage * CONV_STAGE_BYTES;
-            const uint32_t b_dst = a_dst + CONV_A_STAGE;
-            for (int r = 0; r < nwin; ++r) {
-              const int pix0 = p.lead + wi.m0 + (r - sg.ht) * p.Wp - sg.hl;
-#pragma unroll
-              for (int pl = 0; pl < 2; ++pl) {
-                const __nv_bfloat16* src = img + ((long long)(ks * 2 + pl) * p.PL + pix0) * 8;
-                bulk_g2s(a_dst + (uint32_t)((r * 2 + pl) * npix) * 16u, src, (uint32_t)npix * 16u, full);
-              }
-            }
-            const __nv_bfloat16* wsrc =
-                sg.wpack + ((long long)(wi.ntile * sg.ksteps + ks) * sg.ntaps) * (CONV_B_TAP / 2);
-            bulk_g2s(b_dst, wsrc, b_bytes, full);
-            if (++stage == CONV_STAGES) { stage = 0; phase ^= 1; }
+            mbar_arrive_expect_tx(full, tx_bytes);
           }
+          __syncwarp();
+          if (bytes) bulk_g2s(smem_base + stage * CONV_STAGE_BYTES + dst_off, src, bytes, full);
+          src += src_step;
+          if (++stage == CONV_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(CONV_TM, CONV_NT);
-      int stage = 0;
-      uint32_t phase = 0, tphase = 0;
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-        const WorkItem wi = decode_work(p, w);
-        mbar_wait(bar_tempty, tphase ^ 1);  // epilogue has drained the accumulators of the previous item
-        tc_fence_after();
-        bool first = true;
-        for (int s = 0; s < p.nseg; ++s) {
-          const ConvSeg& sg = p.seg[s];
-          const int npix = p.wide ? (CONV_TM + sg.hl + sg.hr)
-                                  : (wi.G * CONV_TM + (sg.ht + sg.hb) * p.Wp + sg.hl + sg.hr);
-          const uint32_t lbo_a = (uint32_t)npix * 16u;
+    // ================================ MMA issuer. The whole warp builds a per-segment table of descriptor offsets
+    // (one entry per (tile, tap)); lane 0 then issues one tcgen05.mma per entry with two shared loads and a few ALU ops.
+    constexpr uint32_t idesc = make_idesc_bf16(CONV_TM, CONV_NT);
+    constexpr uint32_t bdesc_lo_hi = ((CONV_NT / 8) * 128 >> 4) << 16;   // LBO of B
+    constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);               // SBO = 128 B, descriptor version 1
+    int stage = 0;
+    uint32_t phase = 0, tphase = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      const WorkItem wi = decode_work(p, w);
+      bool first = true;
+      for (int s = 0; s < p.nseg; ++s) {
+        const ConvSeg& sg = p.seg[s];
+        const int npix = p.wide ? (CONV_TM + sg.hl + sg.hr)
+                                : (wi.G * CONV_TM + (sg.ht + sg.hb) * p.Wp + sg.hl + sg.hr);
+        const int cnt = wi.G * sg.ntaps;
+        __syncwarp();
+        for (int k = lane; k < cnt; k += 32) {
+          const int i = k / sg.ntaps, t = k - i * sg.ntaps;
+          uint32_t a_off;
+          if (p.wide)
+            a_off = (uint32_t)((i + sg.dh[t] + sg.ht) * 2 * npix + sg.dw[t] + sg.hl);          // 16-byte units
+          else
+            a_off = (uint32_t)(i * CONV_TM + (sg.dh[t] + sg.ht) * p.Wp + sg.dw[t] + sg.hl);
+          mtab[k] = make_uint2(a_off, ((uint32_t)(CONV_A_STAGE + t * CONV_B_TAP) >> 4) | ((uint32_t)i << 16) |
+                                          (t == 0 ? 0x80000000u : 0u));
+        }
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t adesc_lo_hi = ((uint32_t)npix & 0x3FFF) << 16;  // LBO of A = npix * 16 B
+          if (s == 0) {
+            mbar_wait(bar_tempty, tphase ^ 1);  // epilogue has drained the accumulators of the previous item
+            tc_fence_after();
+          }
           for (int ks = 0; ks < sg.ksteps; ++ks) {
             mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
-            const uint32_t a_base = smem_base + stage * CONV_STAGE_BYTES;
-            const uint32_t b_base = a_base + CONV_A_STAGE;
-            for (int i = 0; i < wi.G; ++i) {
-              const uint32_t d = tmem_base + (uint32_t)i * CONV_NT;
-              for (int t = 0; t < sg.ntaps; ++t) {
-                uint32_t a_addr;
-                if (p.wide)
-                  a_addr = a_base + (uint32_t)((i + sg.dh[t] + sg.ht) * 2 * npix + sg.dw[t] + sg.hl) * 16u;
-                else
-                  a_addr = a_base + (uint32_t)(i * CONV_TM + (sg.dh[t] + sg.ht) * p.Wp + sg.dw[t] + sg.hl) * 16u;
-                const uint64_t adesc = make_smem_desc(a_addr, lbo_a, 128);
-                const uint64_t bdesc = make_smem_desc(b_base + t * CONV_B_TAP, (CONV_NT / 8) * 128, 128);
-                umma_bf16(d, adesc, bdesc, idesc, (first && t == 0) ? 0u : 1u);
-              }
+            const uint32_t base16 = (smem_base + stage * CONV_STAGE_BYTES) >> 4;
+#pragma unroll 4
+            for (int k = 0; k < cnt; ++k) {
+              const uint2 e = mtab[k];
+              const uint64_t adesc = ((uint64_t)desc_hi << 32) | (((base16 + e.x) & 0x3FFF) | adesc_lo_hi);
+              const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (((base16 + (e.y & 0xFFFF)) & 0x3FFF) | bdesc_lo_hi);
+              const uint32_t d = tmem_base + ((e.y >> 16) & 0x7) * CONV_NT;
+              umma_bf16(d, adesc, bdesc, idesc, (first && (e.y & 0x80000000u)) ? 0u : 1u);
             }
             first = false;
             umma_commit(bar_empty + 8 * stage);  // frees the stage when these MMAs retire
             if (++stage == CONV_STAGES) { stage = 0; phase ^= 1; }
           }
+        } else {
+          for (int ks = 0; ks < sg.ksteps; ++ks)
+            if (++stage == CONV_STAGES) { stage = 0; phase ^= 1; }
+          first = false;
         }
-        umma_commit(bar_tfull);
-        tphase ^= 1;
       }
+      if (lane == 0) umma_commit(bar_tfull);
+      tphase ^= 1;
     }
   } else if (warp >= 4) {
     // ================================ epilogue: TMEM -> regs -> (+bias,+temb,+residual) -> stats, bf16 store
@@ -181,15 +208,20 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
 
       __nv_bfloat16* out_img = p.out + (long long)wi.n * out_img_stride;
       const __nv_bfloat16* res_img = p.res ? p.res + (long long)wi.n * out_img_stride : nullptr;
-      for (int i = 0; i < wi.G; ++i) {
+      for (int i = 0; i < ((p.dbg & 8) ? 0 : wi.G); ++i) {
         const int m = wi.m0 + i * wi.tile_stride + q * 32 + lane;
         bool valid = true;
         if (!p.wide) valid = (m < hw_end) && ((m % p.Wp) != p.W);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(i * CONV_NT + j * 32), r);
-          tmem_ld_wait();
+          if (!(p.dbg & 4)) {
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(i * CONV_NT + j * 32), r);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) r[e] = 0;
+          }
           float v[32];
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]) + sbias[j * 32 + e];
@@ -211,9 +243,9 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
               o.y = pack_bf16x2(v[c8 * 8 + 2], v[c8 * 8 + 3]);
               o.z = pack_bf16x2(v[c8 * 8 + 4], v[c8 * 8 + 5]);
               o.w = pack_bf16x2(v[c8 * 8 + 6], v[c8 * 8 + 7]);
-              *reinterpret_cast<uint4*>(out_img + off) = o;
+              if (!(p.dbg & 2)) *reinterpret_cast<uint4*>(out_img + off) = o;
             }
-            if (p.stats) {
+            if (p.stats && !(p.dbg & 1)) {
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 const float a = v[4 * k], b = v[4 * k + 1], c = v[4 * k + 2], d = v[4 * k + 3];
@@ -228,9 +260,9 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
       tc_fence_before();
       mbar_arrive(bar_tempty);
 
-      if (p.stats) {
+      if (p.stats && !(p.dbg & 1)) {
         // warp transpose-reduce: 16 values per 32-column chunk -> one lane per value
-        float* sdst = p.stats + ((long long)wi.n * (p.cout >> 2) + wi.ntile * 32) * 2;
+        stat_t* sdst = p.stats + ((long long)wi.n * (p.cout >> 2) + wi.ntile * 32) * 2;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float v16[16];
@@ -251,7 +283,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
           if ((lane & 1) == 0) {
             const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
             const int is_sq = idx >> 3, quad = idx & 7;
-            atomicAdd(sdst + (j * 8 + quad) * 2 + is_sq, tot);
+            atomicAdd(sdst + (j * 8 + quad) * 2 + is_sq, (stat_t)tot);
           }
         }
       }
@@ -263,7 +295,14 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-cudaError_t launch_conv_tc(const ConvParams& p, int num_sms, cudaStream_t stream) {
+cudaError_t launch_conv_tc(const ConvParams& p_in, int num_sms, cudaStream_t stream) {
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("B200AD_CONV_DBG");
+    dbg = e ? atoi(e) : 0;
+  }
+  ConvParams p = p_in;
+  p.dbg = dbg;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_BYTES);

@@ -44,7 +44,8 @@ struct ConvParams {
   const float* temb;            // optional per-sample additive term [N][temb_stride] (offset applied)
   int temb_stride;
   const __nv_bfloat16* res;     // optional residual, PF8 with cout channels
-  float* stats;                 // optional [N][cout/4][2] running (sum, sumsq) of the stored output
+  stat_t* stats;                // optional [N][cout/4][2] running (sum, sumsq) of the stored output
+  int dbg;                      // B200AD_CONV_DBG bit flags (timing experiments only): 1 no stats, 2 no stores, 4 no tmem ld, 8 no epilogue
 };
 
 cudaError_t launch_conv_tc(const ConvParams& p, int num_sms, cudaStream_t stream);

@@ -65,18 +65,18 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
   const int cpg = Ct / p.groups;
   const Geom g = make_geom(p.N, p.H, p.W);
   for (int gi = threadIdx.x; gi < p.groups; gi += blockDim.x) {
-    float s = 0.f, q = 0.f;
+    double s = 0., q = 0.;
     for (int c = gi * cpg; c < (gi + 1) * cpg; c += 4) {
-      const float* st = (c < p.C[0]) ? p.stats[0] + ((long long)n * (p.C[0] >> 2) + (c >> 2)) * 2
+      const stat_t* st = (c < p.C[0]) ? p.stats[0] + ((long long)n * (p.C[0] >> 2) + (c >> 2)) * 2
                                      : p.stats[1] + ((long long)n * (p.C[1] >> 2) + ((c - p.C[0]) >> 2)) * 2;
       s += st[0];
       q += st[1];
     }
-    const float cnt = (float)cpg * (float)p.H * (float)p.W;
-    const float mean = s / cnt;
-    const float var = fmaxf(q / cnt - mean * mean, 0.f);
-    gmean[gi] = mean;
-    grstd[gi] = rsqrtf(var + p.eps);
+    const double cnt = (double)cpg * (double)p.H * (double)p.W;
+    const double mean = s / cnt;
+    const double var = fmax(q / cnt - mean * mean, 0.);
+    gmean[gi] = (float)mean;
+    grstd[gi] = (float)(1.0 / sqrt(var + (double)p.eps));
   }
   __syncthreads();
   for (int c = threadIdx.x; c < Ct; c += blockDim.x) {
@@ -133,7 +133,7 @@ cudaError_t launch_gn_apply(const GnApplyParams& p, cudaStream_t s) {
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ b, int N, int cin, int H, int W,
                                                       int cout, __nv_bfloat16* __restrict__ out,
-                                                      float* __restrict__ stats) {
+                                                      stat_t* __restrict__ stats) {
   __shared__ float red[8][4];
   const Geom g = make_geom(N, H, W);
   const int n = blockIdx.z, pl = blockIdx.y;
@@ -182,14 +182,14 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
       float t = 0.f;
       for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
       // quads 2*pl (values 0,1) and 2*pl+1 (values 2,3)
-      float* dst = stats + ((long long)n * (cout >> 2) + pl * 2 + (threadIdx.x >> 1)) * 2 + (threadIdx.x & 1);
-      atomicAdd(dst, t);
+      stat_t* dst = stats + ((long long)n * (cout >> 2) + pl * 2 + (threadIdx.x >> 1)) * 2 + (threadIdx.x & 1);
+      atomicAdd(dst, (stat_t)t);
     }
   }
 }
 
 cudaError_t launch_conv_in(const float* x, const float* w, const float* b, int N, int cin, int H, int W, int cout,
-                           __nv_bfloat16* out, float* stats, cudaStream_t s) {
+                           __nv_bfloat16* out, stat_t* stats, cudaStream_t s) {
   dim3 grid((H * W + 255) / 256, cout >> 3, N);
   conv_in_kernel<<<grid, 256, 0, s>>>(x, w, b, N, cin, H, W, cout, out, stats);
   return cudaGetLastError();
@@ -215,16 +215,16 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const ConvOutParams p) {
   const int cpg = p.C / p.groups;
 
   for (int gi = threadIdx.x; gi < p.groups; gi += blockDim.x) {
-    float s = 0.f, q = 0.f;
+    double s = 0., q = 0.;
     for (int c = gi * cpg; c < (gi + 1) * cpg; c += 4) {
-      const float* st = p.stats + ((long long)n * (p.C >> 2) + (c >> 2)) * 2;
+      const stat_t* st = p.stats + ((long long)n * (p.C >> 2) + (c >> 2)) * 2;
       s += st[0];
       q += st[1];
     }
-    const float cnt = (float)cpg * (float)p.H * (float)p.W;
-    const float mean = s / cnt;
-    gmean[gi] = mean;
-    grstd[gi] = rsqrtf(fmaxf(q / cnt - mean * mean, 0.f) + p.eps);
+    const double cnt = (double)cpg * (double)p.H * (double)p.W;
+    const double mean = s / cnt;
+    gmean[gi] = (float)mean;
+    grstd[gi] = (float)(1.0 / sqrt(fmax(q / cnt - mean * mean, 0.) + (double)p.eps));
   }
   // weights: fp32 [cout][C][3][3] -> smem [cout][tap][C]
   for (int i = threadIdx.x; i < p.cout * p.C * 9; i += blockDim.x) {
@@ -413,7 +413,7 @@ cudaError_t launch_pf8_to_nchw(const __nv_bfloat16* src, float* dst, int N, int 
 // ------------------------------------------------------------------------------------ standalone quad stats
 // (the hot path gets these from the producing conv's epilogue; this kernel serves tensors that arrive from
 // outside, e.g. the op-level GroupNorm entry point)
-__global__ void __launch_bounds__(256) quad_stats_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ stats,
+__global__ void __launch_bounds__(256) quad_stats_kernel(const __nv_bfloat16* __restrict__ src, stat_t* __restrict__ stats,
                                                          int N, int C, int H, int W) {
   __shared__ float red[8][4];
   const Geom g = make_geom(N, H, W);
@@ -439,14 +439,23 @@ __global__ void __launch_bounds__(256) quad_stats_kernel(const __nv_bfloat16* __
   if (threadIdx.x < 4) {
     float t = 0.f;
     for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
-    atomicAdd(stats + ((long long)n * (C >> 2) + pl * 2 + (threadIdx.x >> 1)) * 2 + (threadIdx.x & 1), t);
+    atomicAdd(stats + ((long long)n * (C >> 2) + pl * 2 + (threadIdx.x >> 1)) * 2 + (threadIdx.x & 1), (stat_t)t);
   }
 }
-cudaError_t launch_quad_stats(const __nv_bfloat16* src, float* stats, int N, int C, int H, int W, cudaStream_t s) {
+cudaError_t launch_quad_stats(const __nv_bfloat16* src, stat_t* stats, int N, int C, int H, int W, cudaStream_t s) {
   int bx = (H * W + 255) / 256;
   if (bx > 64) bx = 64;
   dim3 grid(bx, C >> 3, N);
   quad_stats_kernel<<<grid, 256, 0, s>>>(src, stats, N, C, H, W);
+  return cudaGetLastError();
+}
+
+__global__ void stats_to_float_kernel(const stat_t* s, float* d, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = (float)s[i];
+}
+cudaError_t launch_stats_to_float(const stat_t* s, float* d, int n, cudaStream_t st) {
+  stats_to_float_kernel<<<(n + 255) / 256, 256, 0, st>>>(s, d, n);
   return cudaGetLastError();
 }
 

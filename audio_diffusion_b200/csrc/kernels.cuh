@@ -21,7 +21,7 @@ cudaError_t launch_pack_weights(const float* w, int cout, int cin_total, int KH,
 // stats: running (sum, sumsq) per (n, 4-channel quad) written by the producers' epilogues.
 struct GnApplyParams {
   const __nv_bfloat16* src[2];
-  const float* stats[2];      // [N][C_i/4][2]
+  const stat_t* stats[2];     // [N][C_i/4][2]
   int C[2];                   // channels of each source (C[1] = 0 if single)
   const float* gamma;         // [C0 + C1]
   const float* beta;
@@ -34,7 +34,7 @@ cudaError_t launch_gn_apply(const GnApplyParams& p, cudaStream_t s);
 
 // conv_in: fp32 NCHW (N, cin, H, W), 3x3 pad 1 -> raw bf16 PF8 (cout channels) + quad stats.
 cudaError_t launch_conv_in(const float* x, const float* w, const float* b, int N, int cin, int H, int W, int cout,
-                           __nv_bfloat16* out, float* stats, cudaStream_t s);
+                           __nv_bfloat16* out, stat_t* stats, cudaStream_t s);
 
 // conv_norm_out + SiLU + conv_out (3x3, C -> cout small) fused with the scheduler update.
 // eps_out (optional): model output, fp32 NCHW.  If x_out != null:
@@ -46,7 +46,7 @@ struct StepCoef {
 };
 struct ConvOutParams {
   const __nv_bfloat16* src;   // raw PF8, C channels
-  const float* stats;         // [N][C/4][2]
+  const stat_t* stats;        // [N][C/4][2]
   const float* gamma;
   const float* beta;
   const float* w;             // fp32 [cout][C][3][3]
@@ -65,7 +65,8 @@ cudaError_t launch_conv_out(const ConvOutParams& p, cudaStream_t s);
 cudaError_t launch_upsample2x(const __nv_bfloat16* src, __nv_bfloat16* dst, int N, int C, int H, int W, cudaStream_t s);
 cudaError_t launch_parity_split(const __nv_bfloat16* src, __nv_bfloat16* dst4, int N, int C, int H, int W, cudaStream_t s);
 
-cudaError_t launch_quad_stats(const __nv_bfloat16* src, float* stats, int N, int C, int H, int W, cudaStream_t s);
+cudaError_t launch_quad_stats(const __nv_bfloat16* src, stat_t* stats, int N, int C, int H, int W, cudaStream_t s);
+cudaError_t launch_stats_to_float(const stat_t* s, float* d, int n, cudaStream_t st);
 cudaError_t launch_sample_to_u8(const float* x, uint8_t* img, size_t n, cudaStream_t s);
 
 // layout conversion for tests / debugging

@@ -1,10 +1,359 @@
-// Mel codec kernels (placeholder until the STFT / Griffin-Lim kernels land in this file).
+// Mel codec kernels: batched STFT -> power -> mel -> dB -> uint8 (Mel.audio_slice_to_image, audiodiffusion/mel.py:135-151)
+// and uint8 -> dB -> power -> inverse mel -> 32-iteration Griffin-Lim (Mel.image_to_audio, audiodiffusion/mel.py:153-168).
+// The librosa 0.10.2 arithmetic these follow is restated in oracle/mel_oracle.py.
+//
+// All FFTs run in fp64 (B200 has the fp64 rate to spare; the reference mixes fp64 FFTs with fp32 storage), one
+// frame per CTA, Stockham radix-2 in shared memory. Spectra are kept frame-major so every load is coalesced.
+#include <math_constants.h>
+
 #include "../../include/b200ad.h"
-namespace b200ad { int set_err(const char* fmt, ...); }
-extern "C" size_t b200ad_mel_scratch_bytes(const b200ad_mel_config*, int) { return 0; }
-extern "C" int b200ad_mel_encode(const b200ad_mel_config*, const float*, uint8_t*, int, void*, size_t, void*) {
-  return b200ad::set_err("mel_encode: not built");
+#include "common.cuh"
+
+namespace b200ad {
+int set_err(const char* fmt, ...);
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
-extern "C" int b200ad_mel_decode(const b200ad_mel_config*, const uint8_t*, float*, int, uint64_t, void*, size_t, void*) {
-  return b200ad::set_err("mel_decode: not built");
+__device__ __forceinline__ double hann(int i, int N) {  // periodic Hann, scipy get_window("hann", N, fftbins=True)
+  return 0.5 - 0.5 * cospi(2.0 * (double)i / (double)N);
+}
+
+// twiddles tw[i] = exp(-2 pi i / N), i < N/2
+__global__ void twiddle_kernel(double2* tw, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N / 2) {
+    double s, c;
+    sincospi(-2.0 * (double)i / (double)N, &s, &c);
+    tw[i] = make_double2(c, s);
+  }
+}
+
+// In-place-ish Stockham autosort radix-2 FFT on N points held in shared memory (ping-pong a <-> b).
+// Returns the buffer that holds the result. All threads of the CTA must call it.
+template <bool INVERSE>
+__device__ double2* fft_stockham(double2* a, double2* b, const double2* __restrict__ tw, int N, int logN) {
+  const int half = N >> 1;
+  for (int s = 0; s < logN; ++s) {
+    const int Ns = 1 << s;
+    for (int j = threadIdx.x; j < half; j += blockDim.x) {
+      const int k = j & (Ns - 1);
+      double2 w = __ldg(tw + (size_t)k * (half >> s));
+      if (INVERSE) w.y = -w.y;
+      const double2 v0 = a[j];
+      const double2 v1 = cmul(a[j + half], w);
+      const int j0 = ((j >> s) << (s + 1)) + k;
+      b[j0] = make_double2(v0.x + v1.x, v0.y + v1.y);
+      b[j0 + Ns] = make_double2(v0.x - v1.x, v0.y - v1.y);
+    }
+    __syncthreads();
+    double2* t = a; a = b; b = t;
+  }
+  return a;
+}
+
+struct MelDims {
+  int T, M, F, N, logN, hop, L;  // frames (x_res), mels (y_res), bins, n_fft, log2 n_fft, hop, slice length
+};
+
+// ------------------------------------------------------------------------------------------ encode
+// grid (T, n): one frame. STFT (fp64, rounded to complex64 like librosa), |X|^2 (fp32), mel = M * S (fp32).
+__global__ void __launch_bounds__(256) enc_frame_kernel(const float* __restrict__ audio, const float* __restrict__ basis_t,
+                                                        const double2* __restrict__ tw, float* __restrict__ mel,
+                                                        unsigned* __restrict__ smax, MelDims d) {
+  extern __shared__ __align__(16) uint8_t msm[];
+  double2* a = reinterpret_cast<double2*>(msm);
+  double2* b = a + d.N;
+  float* pw = reinterpret_cast<float*>(b + d.N);
+  const int t = blockIdx.x, n = blockIdx.y;
+  const float* y = audio + (size_t)n * d.L;
+  for (int i = threadIdx.x; i < d.N; i += blockDim.x) {
+    const int p = t * d.hop + i - d.N / 2;
+    const double v = (p >= 0 && p < d.L) ? (double)y[p] : 0.0;
+    a[i] = make_double2(v * hann(i, d.N), 0.0);
+  }
+  __syncthreads();
+  double2* X = fft_stockham<false>(a, b, tw, d.N, d.logN);
+  for (int f = threadIdx.x; f < d.F; f += blockDim.x) {
+    const float re = (float)X[f].x, im = (float)X[f].y;  // stft_matrix is complex64
+    const float mag = hypotf(re, im);                    // np.abs(complex64)
+    pw[f] = mag * mag;                                   // ** 2 in float32
+  }
+  __syncthreads();
+  float lmax = 0.f;
+  for (int m = threadIdx.x; m < d.M; m += blockDim.x) {
+    float acc = 0.f;
+    for (int f = 0; f < d.F; ++f) acc = fmaf(basis_t[(size_t)f * d.M + m], pw[f], acc);
+    mel[((size_t)n * d.M + m) * d.T + t] = acc;
+    lmax = fmaxf(lmax, acc);
+  }
+  // ref = np.max(S): non-negative floats order like their bit patterns
+  for (int sh = 16; sh >= 1; sh >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, sh));
+  if ((threadIdx.x & 31) == 0) atomicMax(smax + n, __float_as_uint(lmax));
+}
+
+// power_to_db(ref=np.max, amin=1e-10, top_db) followed by mel.py:149 (float32 arithmetic, truncating cast)
+__global__ void enc_db_kernel(const float* __restrict__ mel, const unsigned* __restrict__ smax, uint8_t* __restrict__ img,
+                              int per, float top_db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (i >= per) return;
+  const float amin = 1e-10f;
+  const float ref = __uint_as_float(smax[n]);
+  const float s = mel[(size_t)n * per + i];
+  float ls = __fmul_rn(10.0f, (float)log10((double)fmaxf(amin, s)));
+  ls = __fsub_rn(ls, __fmul_rn(10.0f, (float)log10((double)fmaxf(amin, ref))));
+  // log_spec.max() is exactly 0 when ref is the maximum of S
+  ls = fmaxf(ls, __fsub_rn(0.0f, top_db));
+  float v = __fdiv_rn(__fmul_rn(__fadd_rn(ls, top_db), 255.0f), top_db);
+  v = fminf(fmaxf(v, 0.0f), 255.0f);
+  img[(size_t)n * per + i] = (uint8_t)(int)__fadd_rn(v, 0.5f);
+}
+
+// ------------------------------------------------------------------------------------------ decode
+__device__ __forceinline__ double u01(uint64_t seed, uint64_t idx) {  // splitmix64 -> [0,1)
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// inverse mel: X2 = max(pinv(A) * S, 0) (what librosa.util.nnls returns on image-domain inputs: its L-BFGS-B stops at
+// iteration 0), mag = sqrt(X2), angles = mag * exp(2 pi i u).   grid (ceil(F/64), ceil(T/64), n), 256 threads, 4x4 tile.
+__global__ void __launch_bounds__(256) dec_pinv_kernel(const uint8_t* __restrict__ img, const double* __restrict__ pinv,
+                                                       double* __restrict__ mag, double2* __restrict__ ang, MelDims d,
+                                                       double top_db, uint64_t seed) {
+  __shared__ double sp[16][65];  // pinv tile  [k][f]
+  __shared__ double ss[16][65];  // power tile [k][t]
+  const int n = blockIdx.z, f0 = blockIdx.x * 64, t0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // tx -> f, ty -> t
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int k0 = 0; k0 < d.M; k0 += 16) {
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      const int kk = i & 15, ff = i >> 4;  // pinv is [F][M]: consecutive threads read consecutive m
+      const int f = f0 + ff;
+      sp[kk][ff] = (f < d.F) ? pinv[(size_t)f * d.M + k0 + kk] : 0.0;
+    }
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      const int tt = i & 63, kk = i >> 6;  // image is [M][T]: consecutive threads read consecutive t
+      const int t = t0 + tt;
+      double v = 0.0;
+      if (t < d.T) {
+        const double bb = (double)img[((size_t)n * d.M + k0 + kk) * d.T + t];
+        const double ldb = bb * top_db / 255.0 - top_db;  // mel.py:163
+        v = pow(10.0, 0.1 * ldb);                          // librosa.db_to_power
+      }
+      ss[kk][tt] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      double pf[4], st[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { pf[i] = sp[kk][tx + 16 * i]; st[i] = ss[kk][ty + 16 * i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(pf[i], st[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int t = t0 + ty + 16 * j;
+    if (t >= d.T) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int f = f0 + tx + 16 * i;
+      if (f >= d.F) continue;
+      const double m = sqrt(fmax(acc[i][j], 0.0));
+      const size_t o = ((size_t)n * d.T + t) * d.F + f;
+      mag[o] = m;
+      double s, c;
+      sincospi(2.0 * u01(seed, o), &s, &c);
+      ang[o] = make_double2(m * c, m * s);
+    }
+  }
+}
+
+// grid (T, n): frame t of image n: irfft of angles[:, t], times the synthesis window -> frames[n][t][N] (fp32)
+__global__ void __launch_bounds__(256) gl_istft_kernel(const double2* __restrict__ ang, const double2* __restrict__ tw,
+                                                       float* __restrict__ frames, MelDims d) {
+  extern __shared__ __align__(16) uint8_t msm[];
+  double2* a = reinterpret_cast<double2*>(msm);
+  double2* b = a + d.N;
+  const int t = blockIdx.x, n = blockIdx.y;
+  const double2* X = ang + ((size_t)n * d.T + t) * d.F;
+  for (int k = threadIdx.x; k < d.F; k += blockDim.x) {
+    const double2 v = X[k];
+    a[k] = v;
+    if (k > 0 && k < d.N / 2) a[d.N - k] = make_double2(v.x, -v.y);
+  }
+  __syncthreads();
+  double2* x = fft_stockham<true>(a, b, tw, d.N, d.logN);
+  const double inv = 1.0 / (double)d.N;
+  float* out = frames + ((size_t)n * d.T + t) * d.N;
+  for (int i = threadIdx.x; i < d.N; i += blockDim.x) out[i] = (float)(x[i].x * inv * hann(i, d.N));
+}
+
+// overlap-add of the windowed frames at padded position p, normalised by the window sum-square (librosa.istft)
+__device__ __forceinline__ float ola_sample(const float* __restrict__ fr, int p, const MelDims& d) {
+  int f_hi = p / d.hop;
+  if (f_hi > d.T - 1) f_hi = d.T - 1;
+  int f_lo = (p - d.N + d.hop) / d.hop;  // ceil((p - N + 1) / hop) for p - N + 1 >= 0
+  if (p - d.N + 1 <= 0) f_lo = 0;
+  double acc = 0.0, wss = 0.0;
+  for (int f = f_lo; f <= f_hi; ++f) {
+    const int i = p - f * d.hop;
+    if (i < 0 || i >= d.N) continue;
+    acc += (double)fr[(size_t)f * d.N + i];
+    const double w = hann(i, d.N);
+    wss += w * w;
+  }
+  const float y = (float)acc, ws = (float)wss;
+  return (ws > 1.17549435e-38f) ? __fdiv_rn(y, ws) : y;
+}
+
+// grid (T, n): STFT of the re-synthesised signal for frame t, then the fast Griffin-Lim phase update
+//   angles = rebuilt - momentum/(1+momentum) * tprev;  angles /= |angles| + tiny;  angles *= mag;  tprev = rebuilt
+__global__ void __launch_bounds__(256) gl_stft_update_kernel(const float* __restrict__ frames, const double2* __restrict__ tw,
+                                                             const double* __restrict__ mag, double2* __restrict__ ang,
+                                                             float2* __restrict__ tprev, int have_prev, MelDims d) {
+  extern __shared__ __align__(16) uint8_t msm[];
+  double2* a = reinterpret_cast<double2*>(msm);
+  double2* b = a + d.N;
+  const int t = blockIdx.x, n = blockIdx.y;
+  const float* fr = frames + (size_t)n * d.T * d.N;
+  const int p_lo = d.N / 2, p_hi = d.N / 2 + (d.T - 1) * d.hop;  // trimmed signal occupies padded [p_lo, p_hi)
+  for (int i = threadIdx.x; i < d.N; i += blockDim.x) {
+    const int p = t * d.hop + i;
+    const double v = (p >= p_lo && p < p_hi) ? (double)ola_sample(fr, p, d) : 0.0;
+    a[i] = make_double2(v * hann(i, d.N), 0.0);
+  }
+  __syncthreads();
+  double2* X = fft_stockham<false>(a, b, tw, d.N, d.logN);
+  const double mom = 0.99 / 1.99;
+  for (int f = threadIdx.x; f < d.F; f += blockDim.x) {
+    const size_t o = ((size_t)n * d.T + t) * d.F + f;
+    const float2 rb = make_float2((float)X[f].x, (float)X[f].y);  // rebuilt is complex64
+    double re = (double)rb.x, im = (double)rb.y;
+    if (have_prev) {
+      const float2 tp = tprev[o];
+      re -= mom * (double)tp.x;
+      im -= mom * (double)tp.y;
+    }
+    const double den = hypot(re, im) + 2.2250738585072014e-308;
+    const double m = mag[o];
+    ang[o] = make_double2(re / den * m, im / den * m);
+    tprev[o] = rb;
+  }
+}
+
+__global__ void gl_out_kernel(const float* __restrict__ frames, float* __restrict__ audio, MelDims d) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  const int len = (d.T - 1) * d.hop;
+  if (j >= len) return;
+  audio[(size_t)n * len + j] = ola_sample(frames + (size_t)n * d.T * d.N, j + d.N / 2, d);
+}
+
+static int mel_dims(const b200ad_mel_config* c, MelDims* d) {
+  if (!c) return set_err("mel: null config");
+  int logN = 0;
+  while ((1 << logN) < c->n_fft) ++logN;
+  if ((1 << logN) != c->n_fft || c->n_fft < 64 || c->n_fft > 4096) return set_err("mel: n_fft must be a power of two in [64, 4096]");
+  if (c->hop_length <= 0 || c->hop_length > c->n_fft) return set_err("mel: hop_length out of range");
+  d->T = c->x_res; d->M = c->y_res; d->N = c->n_fft; d->logN = logN; d->F = c->n_fft / 2 + 1; d->hop = c->hop_length;
+  d->L = c->x_res * c->hop_length - 1;
+  return 0;
+}
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace b200ad
+using namespace b200ad;
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) return set_err("%s: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+extern "C" size_t b200ad_mel_scratch_bytes(const b200ad_mel_config* c, int n) {
+  MelDims d;
+  if (mel_dims(c, &d)) return 0;
+  const size_t spec = (size_t)n * d.T * d.F;
+  size_t b = al256((size_t)(d.N / 2) * 16);                    // twiddles
+  const size_t enc = al256((size_t)n * d.M * d.T * 4) + al256((size_t)n * 4);
+  const size_t dec = al256(spec * 8) + al256(spec * 16) + al256(spec * 8) + al256((size_t)n * d.T * d.N * 4);
+  return b + (enc > dec ? enc : dec);
+}
+
+static int fft_smem_attr(const void* fn, size_t smem) {
+  CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return 0;
+}
+
+extern "C" int b200ad_mel_encode(const b200ad_mel_config* c, const float* basis_t, const float* audio, uint8_t* images,
+                                 int n, void* scratch, size_t scratch_bytes, void* stream) {
+  MelDims d;
+  if (mel_dims(c, &d)) return -1;
+  if (scratch_bytes < b200ad_mel_scratch_bytes(c, n)) return set_err("mel_encode: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* sb = (uint8_t*)scratch;
+  double2* tw = (double2*)sb;
+  sb += al256((size_t)(d.N / 2) * 16);
+  float* mel = (float*)sb;
+  sb += al256((size_t)n * d.M * d.T * 4);
+  unsigned* smax = (unsigned*)sb;
+  twiddle_kernel<<<(d.N / 2 + 255) / 256, 256, 0, st>>>(tw, d.N);
+  CK(cudaGetLastError());
+  CK(cudaMemsetAsync(smax, 0, (size_t)n * 4, st));
+  const size_t smem = (size_t)2 * d.N * 16 + (size_t)d.F * 4;
+  if (fft_smem_attr((const void*)enc_frame_kernel, smem)) return -1;
+  enc_frame_kernel<<<dim3(d.T, n), 256, smem, st>>>(audio, basis_t, tw, mel, smax, d);
+  CK(cudaGetLastError());
+  const int per = d.M * d.T;
+  enc_db_kernel<<<dim3((per + 255) / 256, n), 256, 0, st>>>(mel, smax, images, per, (float)c->top_db);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200ad_mel_decode(const b200ad_mel_config* c, const double* pinv, const uint8_t* images, float* audio, int n,
+                                 uint64_t phase_seed, void* scratch, size_t scratch_bytes, void* stream) {
+  MelDims d;
+  if (mel_dims(c, &d)) return -1;
+  if (scratch_bytes < b200ad_mel_scratch_bytes(c, n)) return set_err("mel_decode: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* sb = (uint8_t*)scratch;
+  const size_t spec = (size_t)n * d.T * d.F;
+  double2* tw = (double2*)sb;       sb += al256((size_t)(d.N / 2) * 16);
+  double* mag = (double*)sb;        sb += al256(spec * 8);
+  double2* ang = (double2*)sb;      sb += al256(spec * 16);
+  float2* tprev = (float2*)sb;      sb += al256(spec * 8);
+  float* frames = (float*)sb;
+  twiddle_kernel<<<(d.N / 2 + 255) / 256, 256, 0, st>>>(tw, d.N);
+  CK(cudaGetLastError());
+  dec_pinv_kernel<<<dim3((d.F + 63) / 64, (d.T + 63) / 64, n), 256, 0, st>>>(images, pinv, mag, ang, d, (double)c->top_db,
+                                                                            phase_seed);
+  CK(cudaGetLastError());
+  const size_t smem = (size_t)2 * d.N * 16;
+  if (fft_smem_attr((const void*)gl_istft_kernel, smem)) return -1;
+  if (fft_smem_attr((const void*)gl_stft_update_kernel, smem)) return -1;
+  for (int it = 0; it < c->n_iter; ++it) {
+    gl_istft_kernel<<<dim3(d.T, n), 256, smem, st>>>(ang, tw, frames, d);
+    CK(cudaGetLastError());
+    gl_stft_update_kernel<<<dim3(d.T, n), 256, smem, st>>>(frames, tw, mag, ang, tprev, it > 0 ? 1 : 0, d);
+    CK(cudaGetLastError());
+  }
+  gl_istft_kernel<<<dim3(d.T, n), 256, smem, st>>>(ang, tw, frames, d);
+  CK(cudaGetLastError());
+  const int len = (d.T - 1) * d.hop;
+  gl_out_kernel<<<dim3((len + 255) / 256, n), 256, 0, st>>>(frames, audio, d);
+  CK(cudaGetLastError());
+  return 0;
 }

@@ -37,7 +37,7 @@ struct Param {
 struct Act {  // PF8 activation tensor
   __nv_bfloat16* p = nullptr;
   int C = 0, H = 0, W = 0;
-  float* stats = nullptr;
+  stat_t* stats = nullptr;
 };
 
 enum OpKind { OP_TEMB, OP_CONV_IN, OP_GN, OP_CONV, OP_UPSAMPLE, OP_PARITY, OP_ATTN, OP_CONV_OUT };
@@ -94,7 +94,7 @@ struct b200ad_unet {
   size_t ws_bytes = 0;
   std::vector<Op> plan;
   std::map<std::string, Act> taps;
-  float* stats_arena = nullptr;
+  stat_t* stats_arena = nullptr;
   size_t stats_bytes = 0;
   float* temb_act = nullptr;
   float* temb_proj = nullptr;
@@ -390,7 +390,7 @@ struct Builder {
     a.C = C; a.H = H; a.W = W;
     const Geom g = make_geom(N, H, W);
     a.p = (__nv_bfloat16*)ws.take((size_t)N * (C / 8) * g.PL * 16);
-    if (stats) a.stats = (float*)st.take((size_t)N * (C / 4) * 2 * 4);
+    if (stats) a.stats = (stat_t*)st.take((size_t)N * (C / 4) * 2 * sizeof(stat_t));
     return a;
   }
   Act pooled(const std::string& tag, int C, int H, int W, bool stats) {
@@ -399,7 +399,7 @@ struct Builder {
     auto it = pool.find(key);
     if (it == pool.end()) it = pool.emplace(key, alloc(C, H, W, false)).first;
     Act a = it->second;
-    if (stats) a.stats = (float*)st.take((size_t)N * (C / 4) * 2 * 4);
+    if (stats) a.stats = (stat_t*)st.take((size_t)N * (C / 4) * 2 * sizeof(stat_t));
     return a;
   }
   const float* P(const std::string& name) const { return h->pptr[h->pidx.at(name)]; }
@@ -702,7 +702,7 @@ static int build_plan(b200ad_unet* h, uint8_t* ws_base, int N, int H, int W, siz
   if (ws_bytes_out) *ws_bytes_out = (B.ws.off + 255) & ~(size_t)255;
   if (ws_base) {
     h->plan = plan;
-    h->stats_arena = (float*)ws_base;
+    h->stats_arena = (stat_t*)ws_base;
     h->stats_bytes = stats_bytes;
   }
   return 0;
@@ -715,7 +715,7 @@ extern "C" size_t b200ad_unet_workspace_bytes(const b200ad_unet* hc, int N, int 
   // dry run on a scratch copy of the mutable plan state
   auto saved_plan = h->plan;
   auto saved_taps = h->taps;
-  float* sa = h->stats_arena; size_t sb = h->stats_bytes; float* ta = h->temb_act; float* tp = h->temb_proj;
+  stat_t* sa = h->stats_arena; size_t sb = h->stats_bytes; float* ta = h->temb_act; float* tp = h->temb_proj;
   uint8_t* saved_packed = h->packed;
   std::vector<const float*> saved_pptr = h->pptr;
   size_t bytes = 0;
@@ -803,6 +803,47 @@ static int run_plan(b200ad_unet* h, const float* x, const float* t, const float*
   }
   h->last_launches = launches;
   return 0;
+}
+
+// One step with a CUDA event pair around every launch of the plan (device time per op, on `stream`).
+extern "C" int b200ad_unet_profile_step(b200ad_unet* h, const float* x, const float* t, const float* z,
+                                        const b200ad_step_coef* coef, float* x_out, float* op_ms, int* op_kind,
+                                        double* op_flops, int max_ops, void* stream) {
+  if (h->plan.empty()) return set_err("bind_workspace must be called before profile_step");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nops = (int)h->plan.size();
+  if (nops > max_ops) return set_err("profile_step: %d ops > max_ops %d", nops, max_ops);
+  std::vector<cudaEvent_t> ev(nops + 1);
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  std::vector<Op> saved = h->plan;
+  CK(cudaMemsetAsync(h->stats_arena, 0, h->stats_bytes, st));
+  for (int i = 0; i < nops; ++i) {
+    // run a one-op plan between two events (the stats memset of run_plan is skipped by clearing stats_bytes)
+    CK(cudaEventRecord(ev[i], st));
+    h->plan.assign(1, saved[i]);
+    const size_t sb = h->stats_bytes;
+    h->stats_bytes = 0;
+    const int rc = run_plan(h, x, t, z, coef, x_out, nullptr, st);
+    h->stats_bytes = sb;
+    if (rc) { h->plan = saved; return rc; }
+  }
+  CK(cudaEventRecord(ev[nops], st));
+  h->plan = saved;
+  CK(cudaStreamSynchronize(st));
+  for (int i = 0; i < nops; ++i) {
+    CK(cudaEventElapsedTime(&op_ms[i], ev[i], ev[i + 1]));
+    op_kind[i] = (int)saved[i].kind;
+    double fl = 0;
+    if (saved[i].kind == OP_CONV) {
+      const ConvParams& p = saved[i].conv;
+      double k = 0;
+      for (int s = 0; s < p.nseg; ++s) k += (double)p.seg[s].ntaps * p.seg[s].ksteps * 16;
+      fl = 2.0 * p.N * p.H * p.W * p.cout * k;
+    }
+    op_flops[i] = fl;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return nops;
 }
 
 extern "C" int b200ad_unet_forward(b200ad_unet* h, const float* x, const float* t, float* eps_out, void* stream) {

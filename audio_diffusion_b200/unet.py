@@ -190,13 +190,19 @@ class UNet2DModel(nn.Module):
             raise ValueError("timestep must be a scalar or have one entry per sample")
         return t.contiguous()
 
+    def _check_input(self, sample: torch.Tensor) -> torch.Tensor:
+        _lib.require_cuda()
+        if sample.device.type != "cuda":
+            raise _lib.B200ADError("UNet2DModel(b200): input must be a CUDA tensor (no CPU fallback)")
+        return sample.to(torch.float32).contiguous()
+
     # ------------------------------------------------------------------ public call
     def forward(self, sample: torch.Tensor, timestep, return_dict: bool = True):
         """ε = unet(sample, timestep)["sample"] — pipeline_audio_diffusion.py:163."""
         if sample.requires_grad or (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
                                     and self.training):
             raise NotImplementedError("UNet2DModel(b200): the backward pass is not built yet (inference only)")
-        x = sample.to(torch.float32).contiguous()
+        x = self._check_input(sample)
         n, _, hh, ww = x.shape
         with torch.cuda.device(x.device):
             self._ensure_bound(n, hh, ww)
@@ -212,7 +218,7 @@ class UNet2DModel(nn.Module):
     def forward_step(self, sample: torch.Tensor, timestep, coef: StepCoefC, noise: Optional[torch.Tensor] = None,
                      out: Optional[torch.Tensor] = None, want_eps: bool = False):
         """Fused `scheduler.step(unet(sample, t), t, sample)["prev_sample"]` (pipeline_audio_diffusion.py:163-179)."""
-        x = sample.to(torch.float32).contiguous()
+        x = self._check_input(sample)
         n, _, hh, ww = x.shape
         with torch.cuda.device(x.device):
             self._ensure_bound(n, hh, ww)

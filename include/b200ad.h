@@ -82,6 +82,13 @@ int b200ad_unet_forward_step(b200ad_unet* h, const float* x, const float* t, con
  * Returns the number of channels, or negative. dst may be NULL to query (dims[0..2] = C, H, W). */
 int b200ad_unet_debug_tensor(b200ad_unet* h, const char* name, float* dst, int* dims, void* stream);
 
+/* Profiling: run one fused step with a CUDA-event pair around every launch of the plan; fills per-op device time
+ * (ms), op kind (0 temb, 1 conv_in, 2 gn_apply, 3 conv_tc, 4 upsample, 5 parity, 6 attention, 7 conv_out) and, for
+ * conv_tc launches, the algorithmic FLOPs (2*N*H*W*cout*K). Synchronises the stream. Returns the number of ops. */
+int b200ad_unet_profile_step(b200ad_unet* h, const float* x, const float* t, const float* z,
+                             const b200ad_step_coef* coef, float* x_out, float* op_ms, int* op_kind,
+                             double* op_flops, int max_ops, void* stream);
+
 /* Number of kernel launches the last forward enqueued. */
 int b200ad_unet_last_launch_count(const b200ad_unet* h);
 
@@ -102,13 +109,16 @@ typedef struct {
   int x_res, y_res, sample_rate, n_fft, hop_length, top_db, n_iter;
 } b200ad_mel_config;
 size_t b200ad_mel_scratch_bytes(const b200ad_mel_config* cfg, int n);
-/* audio [n][x_res*hop_length - 1] fp32 (device) -> uint8 images [n][y_res][x_res] (device). mel.py:145-149 */
-int b200ad_mel_encode(const b200ad_mel_config* cfg, const float* audio, uint8_t* images, int n,
-                      void* scratch, size_t scratch_bytes, void* stream);
+/* audio [n][x_res*hop_length - 1] fp32 (device) -> uint8 images [n][y_res][x_res] (device). mel.py:145-149.
+ * mel_basis_t: librosa.filters.mel(sr, n_fft, n_mels=y_res) transposed, fp32 [n_fft/2+1][y_res] (device; a
+ * data-independent constant the caller builds once). */
+int b200ad_mel_encode(const b200ad_mel_config* cfg, const float* mel_basis_t, const float* audio, uint8_t* images,
+                      int n, void* scratch, size_t scratch_bytes, void* stream);
 /* uint8 images [n][y_res][x_res] -> audio [n][(x_res-1)*hop_length] fp32. mel.py:162-167.
+ * mel_pinv: numpy.linalg.pinv(mel basis in fp64), fp64 [n_fft/2+1][y_res] (device constant).
  * phase_seed seeds the Griffin-Lim random phase (the reference leaves it unseeded). */
-int b200ad_mel_decode(const b200ad_mel_config* cfg, const uint8_t* images, float* audio, int n, uint64_t phase_seed,
-                      void* scratch, size_t scratch_bytes, void* stream);
+int b200ad_mel_decode(const b200ad_mel_config* cfg, const double* mel_pinv, const uint8_t* images, float* audio, int n,
+                      uint64_t phase_seed, void* scratch, size_t scratch_bytes, void* stream);
 
 /* float sample -> uint8 image, pipeline_audio_diffusion.py:192-194: round-half-even((x/2+.5).clamp(0,1)*255). */
 int b200ad_sample_to_u8(const float* x, uint8_t* img, size_t n, void* stream);

@@ -68,13 +68,16 @@ def _hann(n_fft: int) -> np.ndarray:
 
 
 def stft(y: np.ndarray, n_fft: int, hop: int) -> np.ndarray:
-    """librosa.stft(center=True, pad_mode='constant', window='hann', win_length=n_fft)."""
+    """librosa.stft(center=True, pad_mode='constant', window='hann', win_length=n_fft).
+
+    librosa multiplies the frames by the float64 scipy window (no cast), so the FFT itself runs in float64
+    and only the stored matrix is complex64 for float32 input (util.dtype_r2c)."""
     cdtype = np.complex64 if y.dtype == np.float32 else np.complex128
-    win = _hann(n_fft).astype(y.dtype if y.dtype in (np.float32, np.float64) else np.float64)
+    win = _hann(n_fft)
     yp = np.pad(y, (n_fft // 2, n_fft // 2), mode="constant")
     n_frames = 1 + (len(yp) - n_fft) // hop
     idx = np.arange(n_fft)[:, None] + hop * np.arange(n_frames)[None, :]
-    frames = yp[idx] * win[:, None]
+    frames = win[:, None] * yp[idx]
     return scipy.fft.rfft(frames, axis=0).astype(cdtype, copy=False)
 
 
