@@ -66,11 +66,7 @@ extern "C" int b200ad_conv2d(const float* x, const float* w, const float* bias, 
 
   ConvParams p{};
   p.N = N; p.H = Ho; p.W = Wo; p.Wp = go.Wp; p.lead = go.lead; p.PL = go.PL;
-  p.wide = (Wo % 128 == 0) ? 1 : 0;
-  p.groups_per_img = p.wide ? ((Ho + CONV_MAXG - 1) / CONV_MAXG) * (Wo / 128)
-                            : (Ho * go.Wp + CONV_MAXG * CONV_TM - 1) / (CONV_MAXG * CONV_TM);
-  p.cout = cout; p.ntiles_n = cout / 128;
-  p.total_work = N * p.groups_per_img * p.ntiles_n;
+  p.cout = cout;
   p.out = op; p.bias = bias; p.temb = temb; p.temb_stride = cout; p.res = residual ? rp : nullptr;
   p.stats = stats_out ? stp : nullptr;
   const long long img_stride = (long long)(cin / 8) * go.PL * 8;

@@ -6,15 +6,17 @@ namespace b200ad {
 
 constexpr int CONV_NT = 128;        // output-channel tile = MMA N
 constexpr int CONV_TM = 128;        // pixels per MMA tile = MMA M
-constexpr int CONV_MAXG = 4;        // pixel tiles per work item (4 x 128 fp32 columns = all of TMEM)
-constexpr int CONV_STAGES = 3;
 constexpr int CONV_MAXSEG = 4;
 constexpr int CONV_MAXTAPS = 9;
-constexpr int CONV_A_STAGE = 25088;              // >= 6 windows * 2 planes * 130 px * 16 B
 constexpr int CONV_B_TAP = 16 * CONV_NT * 2;     // one tap, 16 input channels: 4096 B
 constexpr int CONV_B_STAGE = CONV_MAXTAPS * CONV_B_TAP;
-constexpr int CONV_STAGE_BYTES = CONV_A_STAGE + CONV_B_STAGE;
-constexpr int CONV_SMEM_BYTES = CONV_STAGES * CONV_STAGE_BYTES + 1024;
+constexpr int CONV_SMEM_MAX = 227 * 1024;
+
+// Kernel configurations (compile-time): pixel tiles per work item, TMEM accumulator stages, smem ring depth.
+//   cfg 0: 4 tiles, 1 accumulator stage  (4 x 128 columns = all of TMEM; weights reused by 4 tiles; epilogue exposed)
+//   cfg 1: 2 tiles, 2 accumulator stages (epilogue of item k overlaps the MMAs of item k+1; twice the weight traffic)
+struct ConvCfg { int maxg, acc, stages; };
+constexpr ConvCfg CONV_CFGS[2] = {{4, 1, 3}, {2, 2, 3}};
 
 // One K-segment: a source tensor (PF8) with its tap set and packed weights. A 3x3 conv is one
 // segment with 9 taps; a fused 1x1 shortcut adds one 1-tap segment per shortcut source; a stride-2
@@ -28,13 +30,15 @@ struct ConvSeg {
   int ht, hb, hl, hr;          // halo rows above / below, pixels left / right
   signed char dh[CONV_MAXTAPS];
   signed char dw[CONV_MAXTAPS];
+  int aoff[CONV_MAXTAPS];      // (dh + ht) * Wp + dw + hl, filled in by launch_conv_tc: window offset of each tap
 };
 
 struct ConvParams {
   ConvSeg seg[CONV_MAXSEG];
   int nseg;
   int N, H, W, Wp, lead, PL;
-  int wide;             // 1: W % 128 == 0 (tiles = 128-px row pieces stacked over 4 rows); 0: flat
+  int maxg;             // pixel tiles per work item (set by the launcher from the chosen configuration)
+  int a_stage;          // bytes reserved for the A strips of one stage (set by the launcher)
   int groups_per_img;
   int ntiles_n;         // cout / 128
   int total_work;       // N * groups_per_img * ntiles_n

@@ -411,12 +411,7 @@ struct Builder {
   void conv_common(ConvParams& p, const Act& out) {
     const Geom g = make_geom(N, out.H, out.W);
     p.N = N; p.H = out.H; p.W = out.W; p.Wp = g.Wp; p.lead = g.lead; p.PL = g.PL;
-    p.wide = (out.W % 128 == 0) ? 1 : 0;
-    p.groups_per_img = p.wide ? ((out.H + CONV_MAXG - 1) / CONV_MAXG) * (out.W / 128)
-                              : (out.H * g.Wp + CONV_MAXG * CONV_TM - 1) / (CONV_MAXG * CONV_TM);
-    p.cout = out.C;
-    p.ntiles_n = out.C / 128;
-    p.total_work = N * p.groups_per_img * p.ntiles_n;
+    p.cout = out.C;  // work decomposition (tiles per item, item count) is filled in by launch_conv_tc
     p.out = out.p;
     p.stats = out.stats;
   }
