@@ -69,6 +69,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Warp-collective wait: every lane polls and the loop exits on a *vote*, so the exit condition is warp-uniform and the
+// compiler can keep the code that follows on the uniform datapath (no R2UR per tcgen05.mma operand).
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
+  long long t0 = clock64();
+  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+    if (clock64() - t0 > 4000000000LL) {
+      if ((threadIdx.x & 31) == 0) printf("b200ad: mbarrier timeout (block %d warp %d bar %u parity %u)\n", blockIdx.x, threadIdx.x >> 5, bar, parity);
+      __trap();
+    }
+  }
+}
+
 // ------------------------------------------------------------------------ bulk async copy (TMA)
 // 1-D global -> shared bulk copy completing on an mbarrier. 16-byte aligned, size % 16 == 0.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
       const WorkItem wi = decode_work(p, w);
       const int acc = item % ACC;
       const uint32_t d0 = tmem_base + (uint32_t)acc * (MAXG * CONV_NT);
-      mbar_wait(bar_tempty + 8 * acc, (((uint32_t)(item / ACC)) & 1) ^ 1);  // epilogue drained this accumulator
+      mbar_wait_warp(bar_tempty + 8 * acc, (((uint32_t)(item / ACC)) & 1) ^ 1);  // epilogue drained this accumulator
       tc_fence_after();
       uint32_t fresh = 1;  // first k-step of the item overwrites the accumulators
       for (int s = 0; s < p.nseg; ++s) {
@@ -137,10 +137,10 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         const uint32_t adesc_lo_hi = ((uint32_t)npix & 0x3FFF) << 16;  // LBO of A = npix * 16 B
         const int ntaps = sg.ntaps;
         for (int ks = 0; ks < sg.ksteps; ++ks) {
-          mbar_wait(bar_full + 8 * stage, phase);
+          mbar_wait_warp(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t base16 = (smem_base + stage * stage_bytes) >> 4;
-          if (!(p.dbg & 32)) {
+          if (!(p.dbg & 32) && elect_one()) {
             for (int t = 0; t < ntaps; ++t) {
               const uint32_t a_lo = (base16 + (uint32_t)sg.aoff[t]) | adesc_lo_hi;
               const uint64_t bdesc = desc_hi | (uint64_t)((base16 + b_off16 + (uint32_t)t * (CONV_B_TAP >> 4)) | bdesc_lo_hi);
@@ -148,10 +148,11 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
 #pragma unroll
               for (int i = 0; i < MAXG; ++i) {
                 if (i < wi.G)
-                  umma_bf16_elect(d0 + i * CONV_NT, desc_hi | (uint64_t)(a_lo + i * (CONV_TM * 16 >> 4)), bdesc, idesc, accum);
+                  umma_bf16(d0 + i * CONV_NT, desc_hi | (uint64_t)(a_lo + i * (CONV_TM * 16 >> 4)), bdesc, idesc, accum);
               }
             }
           }
+          __syncwarp();
           fresh = 0;
           umma_commit_elect(bar_empty + 8 * stage);  // frees the stage when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -316,7 +317,7 @@ cudaError_t launch_conv_tc(const ConvParams& p_in, int num_sms, cudaStream_t str
     const char* e = getenv("B200AD_CONV_DBG");
     dbg = e ? atoi(e) : 0;
     const char* c = getenv("B200AD_CONV_CFG");
-    cfg_env = c ? atoi(c) : 0;
+    cfg_env = c ? atoi(c) : 1;
     if (cfg_env < 0 || cfg_env > 1) cfg_env = 0;
   }
   ConvParams p = p_in;
