@@ -20,7 +20,7 @@ using namespace b200ad;
 static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct ConvScratch {
-  size_t x, par, res, out, wpack, stats, total;
+  size_t x, par, res, out, wpack, ident, stats, instats, ss, total;
 };
 static ConvScratch conv_scratch_layout(int N, int cin, int cout, int H, int W, int K, int stride) {
   ConvScratch s{};
@@ -33,7 +33,10 @@ static ConvScratch conv_scratch_layout(int N, int cin, int cout, int H, int W, i
   s.res = off; off = al(off + (size_t)N * (cout / 8) * go.PL * 16);
   s.out = off; off = al(off + (size_t)N * (cout / 8) * go.PL * 16);
   s.wpack = off; off = al(off + (size_t)(cout / 128) * (cin / 16) * K * K * CONV_B_TAP);
+  s.ident = off; off = al(off + (size_t)(cout / 128) * (cout / 16) * CONV_B_TAP);
   s.stats = off; off = al(off + (size_t)N * (cout / 4) * 2 * sizeof(stat_t));
+  s.instats = off; off = al(off + (size_t)N * (cin / 4) * 2 * sizeof(stat_t));
+  s.ss = off; off = al(off + (size_t)N * cin * sizeof(float2));
   s.total = off;
   return s;
 }
@@ -42,12 +45,14 @@ extern "C" size_t b200ad_conv2d_scratch_bytes(int N, int cin, int cout, int H, i
   return conv_scratch_layout(N, cin, cout, H, W, K, stride).total;
 }
 
-extern "C" int b200ad_conv2d(const float* x, const float* w, const float* bias, const float* temb, const float* residual,
-                             float* y, float* stats_out, int N, int cin, int cout, int H, int W, int K, int stride,
-                             void* scratch, size_t scratch_bytes, void* stream) {
+static int conv2d_impl(const float* x, const float* w, const float* bias, const float* temb, const float* residual,
+                       float* y, float* stats_out, int N, int cin, int cout, int H, int W, int K, int stride,
+                       const float* gn_gamma, const float* gn_beta, int gn_groups, float gn_eps, int gn_silu,
+                       void* scratch, size_t scratch_bytes, void* stream) {
   if (cin % 16 || cout % 128) return set_err("conv2d: cin %% 16 and cout %% 128 must be 0");
   if (!((K == 3 || K == 1) && (stride == 1 || (stride == 2 && K == 3)))) return set_err("conv2d: unsupported K/stride");
   if (stride == 2 && (H % 2 || W % 2)) return set_err("conv2d: stride 2 needs even H, W");
+  if (stride == 2 && (residual || gn_gamma)) return set_err("conv2d: residual / fused GroupNorm need stride 1");
   const ConvScratch L = conv_scratch_layout(N, cin, cout, H, W, K, stride);
   if (scratch_bytes < L.total) return set_err("conv2d: scratch too small");
   cudaStream_t st = (cudaStream_t)stream;
@@ -67,7 +72,7 @@ extern "C" int b200ad_conv2d(const float* x, const float* w, const float* bias, 
   ConvParams p{};
   p.N = N; p.H = Ho; p.W = Wo; p.Wp = go.Wp; p.lead = go.lead; p.PL = go.PL;
   p.cout = cout;
-  p.out = op; p.bias = bias; p.temb = temb; p.temb_stride = cout; p.res = residual ? rp : nullptr;
+  p.out = op; p.bias = bias; p.temb = temb; p.temb_stride = cout;
   p.stats = stats_out ? stp : nullptr;
   const long long img_stride = (long long)(cin / 8) * go.PL * 8;
   if (stride == 1) {
@@ -79,7 +84,26 @@ extern "C" int b200ad_conv2d(const float* x, const float* w, const float* bias, 
     s.src = xp; s.wpack = wp; s.img_stride = img_stride; s.ksteps = cin / 16; s.ntaps = K * K;
     s.ht = s.hb = s.hl = s.hr = (K == 3) ? 1 : 0;
     for (int k = 0; k < K * K; ++k) { s.dh[k] = (signed char)(k / K - K / 2); s.dw[k] = (signed char)(k % K - K / 2); }
+    s.ss = nullptr; s.ss_stride = 0; s.silu = 0;
     p.nseg = 1;
+    if (gn_gamma) {  // GroupNorm(+SiLU) of x fused into the conv's A staging
+      stat_t* ist = (stat_t*)(sb + L.instats);
+      float2* ss = (float2*)(sb + L.ss);
+      CK(launch_quad_stats(xp, ist, N, cin, H, W, st));
+      GnApplyParams g{};
+      g.src[0] = xp; g.stats[0] = ist; g.C[0] = cin; g.C[1] = 0; g.gamma = gn_gamma; g.beta = gn_beta;
+      g.N = N; g.H = H; g.W = W; g.groups = gn_groups; g.eps = gn_eps;
+      CK(launch_gn_finalize(g, ss, st));
+      s.ss = ss; s.ss_stride = cin; s.silu = gn_silu;
+    }
+    if (residual) {  // residual add = 1-tap identity-weight segment over the raw residual tensor
+      __nv_bfloat16* ident = (__nv_bfloat16*)(sb + L.ident);
+      CK(launch_pack_identity(cout, ident, st));
+      ConvSeg& r = p.seg[1];
+      r.src = rp; r.wpack = ident; r.img_stride = (long long)(cout / 8) * go.PL * 8; r.ksteps = cout / 16; r.ntaps = 1;
+      r.ht = r.hb = r.hl = r.hr = 0; r.dh[0] = 0; r.dw[0] = 0; r.ss = nullptr; r.ss_stride = 0; r.silu = 0;
+      p.nseg = 2;
+    }
   } else {
     CK(launch_parity_split(xp, par, N, cin, H, W, st));
     const size_t tsz = (size_t)N * (cin / 8) * go.PL * 8;
@@ -96,7 +120,7 @@ extern "C" int b200ad_conv2d(const float* x, const float* w, const float* bias, 
         ConvSeg& s = p.seg[a * 2 + b];
         s.src = par + (size_t)(a * 2 + b) * tsz; s.wpack = wseg; s.img_stride = img_stride; s.ksteps = cin / 16;
         s.ntaps = t.ntaps;
-        s.ht = a; s.hb = 0; s.hl = b; s.hr = 0;
+        s.ht = a; s.hb = 0; s.hl = b; s.hr = 0; s.ss = nullptr; s.ss_stride = 0; s.silu = 0;
         for (int k = 0; k < t.ntaps; ++k) { s.dh[k] = (t.kh[k] == 0) ? -1 : 0; s.dw[k] = (t.kw[k] == 0) ? -1 : 0; }
       }
     p.nseg = 4;
@@ -108,6 +132,21 @@ extern "C" int b200ad_conv2d(const float* x, const float* w, const float* bias, 
   CK(launch_pf8_to_nchw(op, y, N, cout, Ho, Wo, st));
   if (stats_out) CK(launch_stats_to_float(stp, stats_out, N * (cout / 4) * 2, st));
   return 0;
+}
+
+extern "C" int b200ad_conv2d(const float* x, const float* w, const float* bias, const float* temb, const float* residual,
+                             float* y, float* stats_out, int N, int cin, int cout, int H, int W, int K, int stride,
+                             void* scratch, size_t scratch_bytes, void* stream) {
+  return conv2d_impl(x, w, bias, temb, residual, y, stats_out, N, cin, cout, H, W, K, stride, nullptr, nullptr, 0, 0.f, 0,
+                     scratch, scratch_bytes, stream);
+}
+
+extern "C" int b200ad_gn_conv2d(const float* x, const float* gamma, const float* beta, int groups, float eps, int silu,
+                                const float* w, const float* bias, float* y, int N, int cin, int cout, int H, int W, int K,
+                                void* scratch, size_t scratch_bytes, void* stream) {
+  if (!gamma || !beta) return set_err("gn_conv2d: gamma and beta are required");
+  return conv2d_impl(x, w, bias, nullptr, nullptr, y, nullptr, N, cin, cout, H, W, K, 1, gamma, beta, groups, eps, silu,
+                     scratch, scratch_bytes, stream);
 }
 
 extern "C" int b200ad_group_norm(const float* x, const float* gamma, const float* beta, float* y, int N, int C, int H,

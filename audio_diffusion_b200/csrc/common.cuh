@@ -90,6 +90,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
       ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 // ------------------------------------------------------------------------------------ tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -171,7 +175,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// generic-proxy writes to shared memory -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // --------------------------------------------------------------------------------- small math
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// silu(x) = x * sigmoid(x) = x * (0.5 + 0.5 * tanh(x / 2)): one MUFU per element
+__device__ __forceinline__ float silu_tanh(float x) { return x * fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -31,6 +31,11 @@ struct ConvSeg {
   signed char dh[CONV_MAXTAPS];
   signed char dw[CONV_MAXTAPS];
   int aoff[CONV_MAXTAPS];      // (dh + ht) * Wp + dw + hl, filled in by launch_conv_tc: window offset of each tap
+  // Fused GroupNorm(+SiLU) of this source, applied to the A strips in shared memory before the MMAs read them:
+  // value = silu?(x * ss[n][c].x + ss[n][c].y), forced to 0 on pad / guard positions. nullptr: source is used as is.
+  const float2* ss;            // [N][ss_stride] (pointer already offset to this source's first channel)
+  int ss_stride;
+  int silu;
 };
 
 struct ConvParams {
@@ -47,11 +52,14 @@ struct ConvParams {
   const float* bias;            // [cout]
   const float* temb;            // optional per-sample additive term [N][temb_stride] (offset applied)
   int temb_stride;
-  const __nv_bfloat16* res;     // optional residual, PF8 with cout channels
   stat_t* stats;                // optional [N][cout/4][2] running (sum, sumsq) of the stored output
   int dbg;                      // B200AD_CONV_DBG bit flags (timing experiments only): 1 no stats, 2 no stores, 4 no tmem ld, 8 no epilogue
 };
 
 cudaError_t launch_conv_tc(const ConvParams& p, int num_sms, cudaStream_t stream);
+
+// Identity weight blocks (W[co][ci] = delta) in the packed layout: a residual add is one extra 1-tap K-segment over the
+// raw source, accumulated by the tensor core (exact: bf16 * 1.0 into fp32).
+cudaError_t launch_pack_identity(int channels, __nv_bfloat16* dst, cudaStream_t s);
 
 }  // namespace b200ad

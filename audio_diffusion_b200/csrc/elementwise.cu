@@ -129,7 +129,45 @@ cudaError_t launch_gn_apply(const GnApplyParams& p, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------ GroupNorm finalize
+// quad sums (one or two concatenated sources) -> per-(sample, channel) scale = gamma * rstd, shift = beta - mean * scale,
+// consumed by the transform warps of conv_tc_kernel.  grid (N), 256 threads.
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const GnApplyParams p, float2* __restrict__ ss) {
+  __shared__ float gmean[64], grstd[64];
+  const int Ct = p.C[0] + p.C[1];
+  const int n = blockIdx.x;
+  const int cpg = Ct / p.groups;
+  for (int gi = threadIdx.x; gi < p.groups; gi += blockDim.x) {
+    double s = 0., q = 0.;
+    for (int c = gi * cpg; c < (gi + 1) * cpg; c += 4) {
+      const stat_t* st = (c < p.C[0]) ? p.stats[0] + ((long long)n * (p.C[0] >> 2) + (c >> 2)) * 2
+                                     : p.stats[1] + ((long long)n * (p.C[1] >> 2) + ((c - p.C[0]) >> 2)) * 2;
+      s += st[0];
+      q += st[1];
+    }
+    const double cnt = (double)cpg * (double)p.H * (double)p.W;
+    const double mean = s / cnt;
+    const double var = fmax(q / cnt - mean * mean, 0.);
+    gmean[gi] = (float)mean;
+    grstd[gi] = (float)(1.0 / sqrt(var + (double)p.eps));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Ct; c += blockDim.x) {
+    const int gi = c / cpg;
+    const float sc = p.gamma[c] * grstd[gi];
+    ss[(long long)n * Ct + c] = make_float2(sc, p.beta[c] - gmean[gi] * sc);
+  }
+}
+cudaError_t launch_gn_finalize(const GnApplyParams& p, float2* ss, cudaStream_t s) {
+  if (p.groups > 64) return cudaErrorInvalidValue;
+  gn_finalize_kernel<<<p.N, 256, 0, s>>>(p, ss);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------ conv_in
+// fp32 NCHW (cin small) -> raw bf16 PF8 + quad statistics. One CTA = one 8-channel plane x 1024 pixels; the 8 x cin x 9
+// weights of the plane sit in registers, each thread produces CI_PIX pixels (HBM-write bound).
+constexpr int CI_PIX = 2;
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ b, int N, int cin, int H, int W,
                                                       int cout, __nv_bfloat16* __restrict__ out,
@@ -137,38 +175,53 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
   __shared__ float red[8][4];
   const Geom g = make_geom(N, H, W);
   const int n = blockIdx.z, pl = blockIdx.y;
-  const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = pidx < H * W;
-  const int h = valid ? pidx / W : 0, ww = valid ? pidx - h * W : 0;
-  float acc[8];
+  float acc[CI_PIX][8];
+  int hh0[CI_PIX], ww0[CI_PIX];
+  bool ok[CI_PIX];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = b[pl * 8 + e];
+  for (int u = 0; u < CI_PIX; ++u) {
+    const int pidx = (blockIdx.x * CI_PIX + u) * blockDim.x + threadIdx.x;
+    ok[u] = pidx < H * W;
+    hh0[u] = ok[u] ? pidx / W : 0;
+    ww0[u] = ok[u] ? pidx - hh0[u] * W : 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[u][e] = __ldg(b + pl * 8 + e);
+  }
   for (int ci = 0; ci < cin; ++ci) {
+    float wr[8][9];
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) wr[e][t] = __ldg(w + ((long long)(pl * 8 + e) * cin + ci) * 9 + t);
     const float* xi = x + ((long long)n * cin + ci) * H * W;
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int hh = h + kh - 1;
+    for (int u = 0; u < CI_PIX; ++u) {
+      float xv[9];
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int wx = ww + kw - 1;
-        const float xv = (valid && hh >= 0 && hh < H && wx >= 0 && wx < W) ? xi[hh * W + wx] : 0.f;
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-          acc[e] = fmaf(xv, __ldg(w + (((long long)(pl * 8 + e) * cin + ci) * 3 + kh) * 3 + kw), acc[e]);
+      for (int t = 0; t < 9; ++t) {
+        const int hh = hh0[u] + t / 3 - 1, wx = ww0[u] + t % 3 - 1;
+        xv[t] = (ok[u] && hh >= 0 && hh < H && wx >= 0 && wx < W) ? __ldg(xi + hh * W + wx) : 0.f;
       }
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[u][e] = fmaf(xv[t], wr[e][t], acc[u][e]);
     }
   }
   float s4[4] = {0.f, 0.f, 0.f, 0.f};
-  if (valid) {
+  __nv_bfloat16* plane = out + ((long long)n * (cout >> 3) + pl) * g.PL * 8;
+#pragma unroll
+  for (int u = 0; u < CI_PIX; ++u) {
+    if (!ok[u]) continue;
+    const float* a = acc[u];
     uint4 o;
-    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
-    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
-    __nv_bfloat16* dp = out + ((long long)n * (cout >> 3) + pl) * g.PL * 8 + (long long)(g.lead + h * g.Wp + ww) * 8;
-    *reinterpret_cast<uint4*>(dp) = o;
-    s4[0] = acc[0] + acc[1] + acc[2] + acc[3];
-    s4[1] = acc[0] * acc[0] + acc[1] * acc[1] + acc[2] * acc[2] + acc[3] * acc[3];
-    s4[2] = acc[4] + acc[5] + acc[6] + acc[7];
-    s4[3] = acc[4] * acc[4] + acc[5] * acc[5] + acc[6] * acc[6] + acc[7] * acc[7];
+    o.x = pack_bf16x2(a[0], a[1]); o.y = pack_bf16x2(a[2], a[3]);
+    o.z = pack_bf16x2(a[4], a[5]); o.w = pack_bf16x2(a[6], a[7]);
+    *reinterpret_cast<uint4*>(plane + (long long)(g.lead + hh0[u] * g.Wp + ww0[u]) * 8) = o;
+    s4[0] += a[0] + a[1] + a[2] + a[3];
+    s4[1] += a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3];
+    s4[2] += a[4] + a[5] + a[6] + a[7];
+    s4[3] += a[4] * a[4] + a[5] * a[5] + a[6] * a[6] + a[7] * a[7];
   }
   if (stats) {
 #pragma unroll
@@ -190,7 +243,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
 
 cudaError_t launch_conv_in(const float* x, const float* w, const float* b, int N, int cin, int H, int W, int cout,
                            __nv_bfloat16* out, stat_t* stats, cudaStream_t s) {
-  dim3 grid((H * W + 255) / 256, cout >> 3, N);
+  dim3 grid((H * W + 256 * CI_PIX - 1) / (256 * CI_PIX), cout >> 3, N);
   conv_in_kernel<<<grid, 256, 0, s>>>(x, w, b, N, cin, H, W, cout, out, stats);
   return cudaGetLastError();
 }
@@ -243,25 +296,41 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const ConvOutParams p) {
   __syncthreads();
   // normalised + SiLU halo tile (zero outside the image: the conv pads the *activated* tensor)
   const __nv_bfloat16* img = p.src + (long long)n * planes * g.PL * 8;
-  for (int i = threadIdx.x; i < planes * CO_HALO * CO_HALO; i += blockDim.x) {
-    const int pl = i / (CO_HALO * CO_HALO);
-    const int hp = i - pl * CO_HALO * CO_HALO;
-    const int hy = hp / CO_HALO, hx = hp - hy * CO_HALO;
-    const int h = h0 + hy - 1, w = w0 + hx - 1;
-    uint4 o = make_uint4(0, 0, 0, 0);
-    if (h >= 0 && h < p.H && w >= 0 && w < p.W) {
-      const uint4 rv = *reinterpret_cast<const uint4*>(img + ((long long)pl * g.PL + g.lead + h * g.Wp + w) * 8);
-      const uint32_t u[4] = {rv.x, rv.y, rv.z, rv.w};
-      uint32_t r[4];
+  constexpr int CO_UNR = 5;   // loads in flight per thread: the halo fill is latency-bound otherwise
+  const int total = planes * CO_HALO * CO_HALO;
+  for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * CO_UNR) {
+    uint4 rv[CO_UNR];
+    bool inb[CO_UNR];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = unpack_bf16x2(u[e]);
-        const int c = pl * 8 + 2 * e;
-        r[e] = pack_bf16x2(silu_f(f.x * scale[c] + shift[c]), silu_f(f.y * scale[c + 1] + shift[c + 1]));
-      }
-      o = make_uint4(r[0], r[1], r[2], r[3]);
+    for (int u = 0; u < CO_UNR; ++u) {
+      const int i = i0 + u * blockDim.x;
+      const int pl = i / (CO_HALO * CO_HALO);
+      const int hp = i - pl * CO_HALO * CO_HALO;
+      const int hy = hp / CO_HALO, hx = hp - hy * CO_HALO;
+      const int h = h0 + hy - 1, w = w0 + hx - 1;
+      inb[u] = (i < total) && h >= 0 && h < p.H && w >= 0 && w < p.W;
+      rv[u] = make_uint4(0, 0, 0, 0);
+      if (inb[u]) rv[u] = *reinterpret_cast<const uint4*>(img + ((long long)pl * g.PL + g.lead + h * g.Wp + w) * 8);
     }
-    act[i] = o;
+#pragma unroll
+    for (int u = 0; u < CO_UNR; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i >= total) continue;
+      uint4 o = make_uint4(0, 0, 0, 0);
+      if (inb[u]) {
+        const int pl = i / (CO_HALO * CO_HALO);
+        const uint32_t uu[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
+        uint32_t r[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_bf16x2(uu[e]);
+          const int c = pl * 8 + 2 * e;
+          r[e] = pack_bf16x2(silu_f(f.x * scale[c] + shift[c]), silu_f(f.y * scale[c + 1] + shift[c + 1]));
+        }
+        o = make_uint4(r[0], r[1], r[2], r[3]);
+      }
+      act[i] = o;
+    }
   }
   __syncthreads();
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;

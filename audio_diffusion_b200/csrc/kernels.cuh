@@ -31,6 +31,9 @@ struct GnApplyParams {
   int silu;
 };
 cudaError_t launch_gn_apply(const GnApplyParams& p, cudaStream_t s);
+// statistics -> per-(sample, channel) (scale, shift) [N][C0 + C1] for the GroupNorm fused into conv_tc_kernel
+// (src / dst / silu of `p` are ignored)
+cudaError_t launch_gn_finalize(const GnApplyParams& p, float2* ss, cudaStream_t s);
 
 // conv_in: fp32 NCHW (N, cin, H, W), 3x3 pad 1 -> raw bf16 PF8 (cout channels) + quad stats.
 cudaError_t launch_conv_in(const float* x, const float* w, const float* b, int N, int cin, int H, int W, int cout,

@@ -50,6 +50,7 @@ struct Op {
   __nv_bfloat16* dst = nullptr;
   int C = 0, H = 0, W = 0;
   ConvOutParams co;
+  float2* ss = nullptr;  // OP_GN: output of gn_finalize
 };
 
 struct Bump {  // two-pass bump allocator: base == nullptr computes sizes only
@@ -85,6 +86,7 @@ struct b200ad_unet {
   size_t packed_bytes = 0;
   size_t off_wcat = 0, off_bcat = 0, off_misc = 0;
   std::map<std::string, size_t> misc_off;  // fused bias vectors (floats)
+  std::map<int, size_t> ident_off;         // channels -> identity weight blocks
   int temb_rows = 0;
   std::map<std::string, int> temb_row_off;
   uint8_t* packed = nullptr;
@@ -234,10 +236,17 @@ static void build_packed_layout(b200ad_unet* h) {
   auto take_off = [&](size_t bytes) { b.take(0); size_t o = (b.off + 255) & ~(size_t)255; b.take(bytes); return o; };
   int out_c = c.block_out_channels[0];
   std::vector<int> skip_c{out_c};
+  h->ident_off.clear();
+  auto need_ident = [&](int ch) {  // identity weight blocks for residual-as-K-segment
+    if (!h->ident_off.count(ch)) h->ident_off[ch] = take_off((size_t)(ch / 128) * (ch / 16) * CONV_B_TAP);
+  };
   auto resnet = [&](const std::string& n, int ca, int cb, int co) {
     const int cin = ca + cb;
-    add_job(h, b, n + ".conv1#0", n + ".conv1.weight", co, cin, 3, 0, cin, taps_3x3());
+    // conv1 over cat(a, b): one K-segment per source (each with its own fused GroupNorm scale/shift slice)
+    add_job(h, b, n + ".conv1#0", n + ".conv1.weight", co, cin, 3, 0, ca, taps_3x3());
+    if (cb) add_job(h, b, n + ".conv1#1", n + ".conv1.weight", co, cin, 3, ca, cb, taps_3x3());
     add_job(h, b, n + ".conv2#0", n + ".conv2.weight", co, co, 3, 0, co, taps_3x3());
+    if (cin == co) need_ident(co);
     if (cin != co) {
       add_job(h, b, n + ".conv2#1", n + ".conv_shortcut.weight", co, cin, 1, 0, ca, taps_1x1());
       if (cb) add_job(h, b, n + ".conv2#2", n + ".conv_shortcut.weight", co, cin, 1, ca, cb, taps_1x1());
@@ -252,6 +261,7 @@ static void build_packed_layout(b200ad_unet* h) {
     add_job(h, b, n + ".qkv#v", n + ".to_v.weight", ch, ch, 1, 0, ch, taps_1x1());
     add_job(h, b, n + ".out#0", n + ".to_out.0.weight", ch, ch, 1, 0, ch, taps_1x1());
     h->misc_off[n + ".bias_qkv"] = take_off((size_t)3 * ch * 4);
+    need_ident(ch);
   };
   for (int i = 0; i < nb; ++i) {
     const int in_c = out_c;
@@ -342,6 +352,7 @@ extern "C" int b200ad_unet_set_params(b200ad_unet* h, const float* const* params
   for (const PackJob& j : h->jobs)
     CK(launch_pack_weights(h->pptr[j.w_param], j.cout, j.cin_total, j.KH, j.KW, j.cin_off, j.ksteps, j.taps,
                            (__nv_bfloat16*)(h->packed + j.off), st));
+  for (const auto& kv : h->ident_off) CK(launch_pack_identity(kv.first, (__nv_bfloat16*)(h->packed + kv.second), st));
   // fused bias vectors
   for (const auto& kv : h->misc_off) {
     const std::string& key = kv.first;
@@ -442,27 +453,39 @@ struct Builder {
     s.wpack = wpack;
     s.img_stride = (long long)(C / 8) * g.PL * 8;
     s.ksteps = C / 16;
+    s.ss = nullptr; s.ss_stride = 0; s.silu = 0;
     seg_taps(s, t, parity, 0, 0);
   }
 
-  void gn(const Act& a, const Act* b, const std::string& norm, const Act& dst, bool silu) {
+  // GroupNorm over cat(a, b): statistics -> per-(sample, channel) scale/shift; the apply itself is fused into the consumer
+  // conv's transform warps. Returns the [N][Ca + Cb] scale/shift array.
+  float2* gn_finalize(const Act& a, const Act* b, const std::string& norm) {
+    const int Ct = a.C + (b ? b->C : 0);
+    float2* ss = (float2*)ws.take((size_t)N * Ct * sizeof(float2));
     Op op{};
     op.kind = OP_GN;
     GnApplyParams& p = op.gn;
     p.src[0] = a.p; p.stats[0] = a.stats; p.C[0] = a.C;
     p.src[1] = b ? b->p : nullptr; p.stats[1] = b ? b->stats : nullptr; p.C[1] = b ? b->C : 0;
     p.gamma = P(norm + ".weight"); p.beta = P(norm + ".bias");
-    p.dst = dst.p;
-    p.N = N; p.H = a.H; p.W = a.W; p.groups = h->cfg.norm_num_groups; p.eps = h->cfg.norm_eps; p.silu = silu ? 1 : 0;
+    p.dst = nullptr;
+    p.N = N; p.H = a.H; p.W = a.W; p.groups = h->cfg.norm_num_groups; p.eps = h->cfg.norm_eps; p.silu = 0;
+    op.ss = ss;
     plan->push_back(op);
+    return ss;
+  }
+  static void seg_norm(ConvSeg& s, const float2* ss, int stride, bool silu) {
+    s.ss = ss; s.ss_stride = stride; s.silu = silu ? 1 : 0;
+  }
+  const __nv_bfloat16* IDENT(int ch) const {
+    return h->packed ? (const __nv_bfloat16*)(h->packed + h->ident_off.at(ch)) : nullptr;
   }
 
   // ResnetBlock2D on x = cat(a, b) (b optional) -> out (raw + stats)
   Act resnet(const std::string& n, const Act& a, const Act* b, int cout, bool out_pooled, const std::string& out_tag) {
     const int cin = a.C + (b ? b->C : 0);
     const int H = a.H, W = a.W;
-    Act n1 = pooled("norm", cin, H, W, false);
-    gn(a, b, n + ".norm1", n1, true);
+    const float2* ss1 = gn_finalize(a, b, n + ".norm1");
     Act h1 = pooled("h1", cout, H, W, true);
     {
       Op op{};
@@ -470,15 +493,19 @@ struct Builder {
       ConvParams& p = op.conv;
       conv_common(p, h1);
       p.nseg = 1;
-      set_seg(p.seg[0], n1.p, cin, H, W, WP(n + ".conv1#0"), taps_3x3());
+      set_seg(p.seg[0], a.p, a.C, H, W, WP(n + ".conv1#0"), taps_3x3());
+      seg_norm(p.seg[0], ss1, cin, true);
+      if (b) {
+        set_seg(p.seg[1], b->p, b->C, H, W, WP(n + ".conv1#1"), taps_3x3());
+        seg_norm(p.seg[1], ss1 + a.C, cin, true);
+        p.nseg = 2;
+      }
       p.bias = P(n + ".conv1.bias");
       p.temb = h->temb_proj + h->temb_row_off.at(n);
       p.temb_stride = h->temb_rows;
-      p.res = nullptr;
       plan->push_back(op);
     }
-    Act n2 = pooled("norm", cout, H, W, false);
-    gn(h1, nullptr, n + ".norm2", n2, true);
+    const float2* ss2 = gn_finalize(h1, nullptr, n + ".norm2");
     Act out = out_pooled ? pooled(out_tag, cout, H, W, true) : alloc(cout, H, W, true);
     {
       Op op{};
@@ -486,10 +513,11 @@ struct Builder {
       ConvParams& p = op.conv;
       conv_common(p, out);
       p.nseg = 1;
-      set_seg(p.seg[0], n2.p, cout, H, W, WP(n + ".conv2#0"), taps_3x3());
+      set_seg(p.seg[0], h1.p, cout, H, W, WP(n + ".conv2#0"), taps_3x3());
+      seg_norm(p.seg[0], ss2, cout, true);
       p.temb = nullptr;
       p.temb_stride = 0;
-      if (cin != cout) {
+      if (cin != cout) {  // 1x1 conv_shortcut over the raw input(s): extra K-segments into the same accumulators
         set_seg(p.seg[1], a.p, a.C, H, W, WP(n + ".conv2#1"), taps_1x1());
         p.nseg = 2;
         if (b) {
@@ -497,10 +525,10 @@ struct Builder {
           p.nseg = 3;
         }
         p.bias = MISC(n + ".bias2");
-        p.res = nullptr;
-      } else {
+      } else {            // identity shortcut: residual add as a 1-tap identity-weight segment over the raw input
+        set_seg(p.seg[1], a.p, a.C, H, W, IDENT(cout), taps_1x1());
+        p.nseg = 2;
         p.bias = P(n + ".conv2.bias");
-        p.res = a.p;
       }
       plan->push_back(op);
     }
@@ -511,8 +539,7 @@ struct Builder {
 
   Act attention(const std::string& n, const Act& x, bool out_pooled, const std::string& out_tag) {
     const int C = x.C, H = x.H, W = x.W;
-    Act nx = pooled("norm", C, H, W, false);
-    gn(x, nullptr, n + ".group_norm", nx, false);
+    const float2* ssx = gn_finalize(x, nullptr, n + ".group_norm");
     Act qkv = pooled("qkv", 3 * C, H, W, false);
     {
       Op op{};
@@ -520,9 +547,10 @@ struct Builder {
       ConvParams& p = op.conv;
       conv_common(p, qkv);
       p.nseg = 1;
-      set_seg(p.seg[0], nx.p, C, H, W, WP(n + ".qkv#q"), taps_1x1());  // q|k|v blocks are contiguous
+      set_seg(p.seg[0], x.p, C, H, W, WP(n + ".qkv#q"), taps_1x1());  // q|k|v blocks are contiguous
+      seg_norm(p.seg[0], ssx, C, false);                               // GroupNorm without SiLU
       p.bias = MISC(n + ".bias_qkv");
-      p.temb = nullptr; p.temb_stride = 0; p.res = nullptr; p.stats = nullptr;
+      p.temb = nullptr; p.temb_stride = 0; p.stats = nullptr;
       plan->push_back(op);
     }
     Act ao = pooled("attn_o", C, H, W, false);
@@ -538,11 +566,11 @@ struct Builder {
       op.kind = OP_CONV;
       ConvParams& p = op.conv;
       conv_common(p, out);
-      p.nseg = 1;
+      p.nseg = 2;
       set_seg(p.seg[0], ao.p, C, H, W, WP(n + ".out#0"), taps_1x1());
+      set_seg(p.seg[1], x.p, C, H, W, IDENT(C), taps_1x1());          // + residual
       p.bias = P(n + ".to_out.0.bias");
       p.temb = nullptr; p.temb_stride = 0;
-      p.res = x.p;
       plan->push_back(op);
     }
     h->taps[n] = out;
@@ -628,7 +656,7 @@ static int build_plan(b200ad_unet* h, uint8_t* ws_base, int N, int H, int W, siz
               B.set_seg(p.seg[a * 2 + b], par.p + (size_t)(a * 2 + b) * tsz, out_c, Ho, Wo,
                         B.WP(n + S("#%d", a * 2 + b)), taps_parity(a, b), true);
           p.bias = B.P(n + ".bias");
-          p.temb = nullptr; p.temb_stride = 0; p.res = nullptr;
+          p.temb = nullptr; p.temb_stride = 0;
           plan.push_back(op);
         }
         h->taps[n] = y;
@@ -674,7 +702,7 @@ static int build_plan(b200ad_unet* h, uint8_t* ws_base, int N, int H, int W, siz
           p.nseg = 1;
           B.set_seg(p.seg[0], up.p, out_c, hh, ww, B.WP(nm + "#0"), taps_3x3());
           p.bias = B.P(nm + ".bias");
-          p.temb = nullptr; p.temb_stride = 0; p.res = nullptr;
+          p.temb = nullptr; p.temb_stride = 0;
           plan.push_back(op);
         }
         h->taps[nm] = y;
@@ -762,7 +790,7 @@ static int run_plan(b200ad_unet* h, const float* x, const float* t, const float*
         ++launches;
         break;
       case OP_GN:
-        CK(launch_gn_apply(op.gn, st));
+        CK(launch_gn_finalize(op.gn, op.ss, st));
         ++launches;
         break;
       case OP_CONV:

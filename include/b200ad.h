@@ -100,6 +100,11 @@ size_t b200ad_conv2d_scratch_bytes(int N, int cin, int cout, int H, int W, int K
 int b200ad_conv2d(const float* x, const float* w, const float* bias, const float* temb, const float* residual,
                   float* y, float* stats_out, int N, int cin, int cout, int H, int W, int K, int stride,
                   void* scratch, size_t scratch_bytes, void* stream);
+/* conv2d(act(GroupNorm(x))) with the GroupNorm(+SiLU) apply fused into the conv kernel's operand staging — the form every
+ * ResnetBlock2D conv takes in the U-Net plan. Stride 1; scratch >= b200ad_conv2d_scratch_bytes(..., stride 1). */
+int b200ad_gn_conv2d(const float* x, const float* gamma, const float* beta, int groups, float eps, int silu,
+                     const float* w, const float* bias, float* y, int N, int cin, int cout, int H, int W, int K,
+                     void* scratch, size_t scratch_bytes, void* stream);
 /* GroupNorm(groups, eps) [+ SiLU] on fp32 NCHW through the stats + apply kernels. */
 int b200ad_group_norm(const float* x, const float* gamma, const float* beta, float* y, int N, int C, int H, int W,
                       int groups, float eps, int silu, void* scratch, size_t scratch_bytes, void* stream);

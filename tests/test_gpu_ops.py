@@ -115,3 +115,33 @@ def test_sample_to_u8_bit_exact(cuda):
     _lib.check(L.b200ad_sample_to_u8(xd.data_ptr(), out.data_ptr(), x.numel(), _lib.stream_ptr()))
     torch.cuda.synchronize()
     assert (out.cpu().numpy() == ref).all()
+
+
+@pytest.mark.parametrize("silu,N,cin,cout,H,W,K", [(1, 2, 128, 128, 32, 32, 3), (0, 1, 256, 128, 16, 16, 1),
+                                                   (1, 1, 128, 256, 8, 128, 3), (1, 2, 384, 128, 16, 16, 3)])
+def test_fused_groupnorm_conv(cuda, silu, N, cin, cout, H, W, K):
+    """conv2d(silu(GroupNorm(x))) with the normalisation applied in the conv kernel's operand staging (transform warps).
+    Reference keeps the normalised tensor in fp32; ours rounds it to bf16 before the MMA: tolerance 2.5e-2 * max|ref|."""
+    from audio_diffusion_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(11)
+    x = _bf(torch.randn(N, cin, H, W, generator=g) * 1.7 + 0.3)
+    gamma = 1 + 0.2 * torch.randn(cin, generator=g)
+    beta = 0.2 * torch.randn(cin, generator=g)
+    w = _bf(torch.randn(cout, cin, K, K, generator=g) / (cin * K * K) ** 0.5)
+    b = torch.randn(cout, generator=g)
+    a = F.group_norm(x, 32, gamma, beta, 1e-5)
+    if silu:
+        a = F.silu(a)
+    ref = F.conv2d(a, w, b, padding=K // 2)
+    d = lambda t: t.to(cuda).contiguous()
+    xd, gd, bd, wd, biasd = d(x), d(gamma), d(beta), d(w), d(b)
+    y = torch.empty(N, cout, H, W, device=cuda)
+    nb = L.b200ad_conv2d_scratch_bytes(N, cin, cout, H, W, K, 1)
+    scratch = torch.empty(nb, dtype=torch.uint8, device=cuda)
+    _lib.check(L.b200ad_gn_conv2d(xd.data_ptr(), gd.data_ptr(), bd.data_ptr(), 32, 1e-5, silu, wd.data_ptr(),
+                                  biasd.data_ptr(), y.data_ptr(), N, cin, cout, H, W, K, scratch.data_ptr(), nb,
+                                  _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    err = (y.cpu() - ref).abs().max().item()
+    assert err <= 2.5e-2 * ref.abs().max().item(), f"err {err} scale {ref.abs().max().item()}"
