@@ -1,33 +1,37 @@
 // tcgen05 implicit-GEMM convolution for the U-Net hot path (replaces the cuDNN conv2d calls that
 // diffusers' UNet2DModel.forward makes; reference call site audiodiffusion/pipeline_audio_diffusion.py:163).
 //
-// GEMM view: D[pixel, cout] = sum over (segment, tap, cin) A[pixel + shift(tap), cin] * W[cout, cin, tap].
-//   M = 128 output pixels (consecutive positions of the PF8 flat sequence), N = 128 output channels,
-//   K = 16 input channels per tcgen05.mma.
-// A operand: the PF8 layout stores 8-channel vectors of consecutive pixels contiguously, which *is* the
-//   K-major no-swizzle UMMA core-matrix layout (8 rows x 16 B). A work item covers MAXG*128 consecutive flat
-//   pixels; per 16 input channels ONE contiguous window per 8-channel plane (the run plus a halo of Wp+1 pixels on
-//   both sides) is bulk-copied (TMA engine, UBLKCP) into shared memory, and every tap of every tile is a
-//   shared-memory descriptor whose start address is shifted by (tile*128 + dh*Wp + dw) * 16 B.
-//   (Measured on B200: a bulk copy costs ~130 cycles of TMA time however small it is, so few large copies.)
-// Fused GroupNorm(+SiLU): the strips hold the RAW producer output; six transform warps rewrite them in place
-//   (x * scale[n][c] + shift[n][c], SiLU via one tanh.approx, zero on pad/guard positions) between the TMA landing
-//   and the MMA reading them, so the normalised tensor never exists in HBM (GroupNorm statistics come from the
-//   producer's epilogue, scale/shift from gn_finalize_kernel).
-// B operand: weights pre-packed on the device into per-(cout tile, 16-channel step, tap) 4 KB blocks; one copy.
+// GEMM view (transposed): D^T[cout, pixel] = sum over (segment, tap, cin) W[cout, cin, tap] * X[pixel + shift(tap), cin].
+//   M = 128 output channels (weights are the A operand), N = up to 256 output pixels (activations are the B operand),
+//   K = 16 input channels per tcgen05.mma.  Why this way round: the kernel is bound by SHARED-MEMORY bandwidth — with
+//   M = N = 128 the two operand reads alone need the full 128 B/clk; N = 256 reads 12 KB per 128-cycle MMA (96 B/clk),
+//   halves the number of MMAs to issue, and the weights of one tap stay latched in the A collector (.collector::a::fill /
+//   ::lastuse) while the second pixel group is multiplied.
+// Pixel operand: the PF8 layout stores 8-channel vectors of consecutive pixels contiguously, which *is* the K-major
+//   no-swizzle UMMA core-matrix layout (8 rows x 16 B). A work item covers MAXG*128 consecutive flat pixels; per 16 input
+//   channels ONE contiguous window per 8-channel plane (the run plus a halo of Wp+1 pixels on both sides) is bulk-copied
+//   (TMA engine, UBLKCP) into shared memory, and every tap is a descriptor whose start address is shifted by
+//   (dh*Wp + dw) * 16 B.  (Measured: a bulk copy costs ~130 cycles of TMA time however small it is -> few large copies.)
+// Fused GroupNorm(+SiLU): the windows hold the RAW producer output; five transform warps rewrite them in place
+//   (x * scale[n][c] + shift[n][c], SiLU via one tanh.approx, zero on pad/guard positions) between the TMA landing and
+//   the MMA reading them, so the normalised tensor never exists in HBM.
+// Weights: pre-packed on the device into per-(cout tile, 16-channel step, tap) 4 KB blocks; a separate, finer ring
+//   (CONV_BT taps per slot) with its own producer warp.
 // Residual adds are an extra 1-tap K-segment with identity weights (exact, and no epilogue loads).
-// Accumulators: MAXG tiles x 128 fp32 columns in TMEM, ACC stages (see ConvCfg).
-// Warp roles (12 warps): 0 bulk-copy producer, 1 MMA issuer (uniform datapath, one elected lane), 2/3/8-11 transform
-//   (warp 2 also owns the TMEM allocation), 4-7 epilogue (bias + timestep embedding,
-//   GroupNorm partial statistics for the consumer, bf16 store).
+// Accumulators: 128 lanes (cout) x MAXG*128 fp32 columns (pixels) in TMEM, ACC stages (see ConvCfg).
+// Warp roles (16 warps): 0 activation producer, 1 MMA issuer (uniform datapath, one elected lane), 3 weight producer,
+//   2/8-11 transform (warp 2 also owns the TMEM allocation), 4-7 + 12-15 epilogue: TMEM -> +bias/temb -> per-channel GroupNorm
+//   partial sums (thread-local) -> bf16 -> 32x32 transpose through shared memory -> coalesced 16-byte PF8 stores.
 #include <cstdlib>
 
 #include "conv_tc.cuh"
 
 namespace b200ad {
 
-constexpr int CONV_THREADS = 384;     // 12 warps
-constexpr int CONV_XF_THREADS = 192;  // transform warps 2, 3, 8, 9, 10, 11
+constexpr int CONV_THREADS = 512;     // 16 warps
+constexpr int CONV_XF_THREADS = 160;  // transform warps 2, 8, 9, 10, 11
+constexpr int CONV_TROW = 80;         // bytes per pixel row of the epilogue transpose tile (32 ch bf16 + 16 B pad)
+constexpr int CONV_TTILE = 32 * CONV_TROW;
 
 struct WorkItem {
   int n, ntile, m0, G;
@@ -65,33 +69,43 @@ __device__ __forceinline__ uint4 xform_vec(uint4 v, const float2 (&ss)[8]) {
   return make_uint4(u[0], u[1], u[2], u[3]);
 }
 
-template <int MAXG, int ACC, int STAGES>
+template <int MAXG, int ACC, int AS, int BS>
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int stage_bytes = p.a_stage + CONV_B_STAGE;
+  const int a_bytes = p.a_stage;
 
-  uint8_t* ctrl = smem + STAGES * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);  // full[S], ready[S], empty[S], tmem_full[ACC], tmem_empty[ACC]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + 120);
-  float* sbias = reinterpret_cast<float*>(ctrl + 128);  // 128 floats
+  uint8_t* bring = smem + AS * a_bytes;                 // weight ring
+  uint8_t* ttile = bring + BS * CONV_B_SLOT;            // 8 epilogue transpose tiles (one per epilogue warp)
+  uint8_t* ctrl = ttile + 8 * CONV_TTILE;
+  // barriers: fullA[AS], readyA[AS], emptyA[AS], fullB[BS], emptyB[BS], tmem_full[ACC], tmem_empty[ACC]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + 504);
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t bar_full = smem_u32(bars);
-  const uint32_t bar_ready = smem_u32(bars + STAGES);
-  const uint32_t bar_empty = smem_u32(bars + 2 * STAGES);
-  const uint32_t bar_tfull = smem_u32(bars + 3 * STAGES);
-  const uint32_t bar_tempty = smem_u32(bars + 3 * STAGES + ACC);
+  const uint32_t bring_base = smem_u32(bring);
+  const uint32_t bar_fullA = smem_u32(bars);
+  const uint32_t bar_readyA = smem_u32(bars + AS);
+  const uint32_t bar_emptyA = smem_u32(bars + 2 * AS);
+  const uint32_t bar_fullB = smem_u32(bars + 3 * AS);
+  const uint32_t bar_emptyB = smem_u32(bars + 3 * AS + BS);
+  const uint32_t bar_tfull = smem_u32(bars + 3 * AS + 2 * BS);
+  const uint32_t bar_tempty = smem_u32(bars + 3 * AS + 2 * BS + ACC);
+  static_assert((3 * AS + 2 * BS + 2 * ACC) * 8 <= 504, "barrier block overflows");
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_ready + 8 * s, CONV_XF_THREADS);
-      mbar_init(bar_empty + 8 * s, 1);
+    for (int s = 0; s < AS; ++s) {
+      mbar_init(bar_fullA + 8 * s, 1);
+      mbar_init(bar_readyA + 8 * s, CONV_XF_THREADS);
+      mbar_init(bar_emptyA + 8 * s, 1);
+    }
+    for (int s = 0; s < BS; ++s) {
+      mbar_init(bar_fullB + 8 * s, 1);
+      mbar_init(bar_emptyB + 8 * s, 1);
     }
     for (int a = 0; a < ACC; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 128);
+      mbar_init(bar_tempty + 8 * a, 256);
     }
     mbar_fence_init();
   }
@@ -102,7 +116,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================================ producer: per stage two A windows (one per 8-channel plane) + one B block
+    // ================================ activation producer: per k-step two windows (one per 8-channel plane), lanes 0 / 1
     int stage = 0;
     uint32_t phase = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
@@ -111,86 +125,109 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
         const ConvSeg& sg = p.seg[s];
         const int npix = wi.G * CONV_TM + (sg.ht + sg.hb) * p.Wp + sg.hl + sg.hr;
         const uint32_t row_bytes = (uint32_t)npix * 16u;
-        const uint32_t b_bytes = (uint32_t)sg.ntaps * CONV_B_TAP;
-        const uint32_t tx_bytes = 2u * row_bytes + b_bytes;
-        const char* src = nullptr;   // this lane's copy: source at k-step 0, byte advance per k-step
-        long long src_step = 0;
-        uint32_t dst_off = 0, bytes = 0;
-        if (lane < 2) {
-          const int pix0 = p.lead + wi.m0 - sg.ht * p.Wp - sg.hl;
-          src = reinterpret_cast<const char*>(sg.src + (long long)wi.n * sg.img_stride + ((long long)lane * p.PL + pix0) * 8);
-          src_step = (long long)2 * p.PL * 16;
-          dst_off = (uint32_t)lane * row_bytes;
-          bytes = row_bytes;
-        } else if (lane == 31) {
-          src = reinterpret_cast<const char*>(sg.wpack + (long long)wi.ntile * sg.ksteps * sg.ntaps * (CONV_B_TAP / 2));
-          src_step = (long long)b_bytes;
-          dst_off = (uint32_t)p.a_stage;
-          bytes = b_bytes;
-        }
+        const int pix0 = p.lead + wi.m0 - sg.ht * p.Wp - sg.hl;
+        const char* src = reinterpret_cast<const char*>(sg.src + (long long)wi.n * sg.img_stride +
+                                                        ((long long)(lane & 1) * p.PL + pix0) * 8);
+        const long long src_step = (long long)2 * p.PL * 16;
         for (int ks = 0; ks < sg.ksteps; ++ks) {
-          const uint32_t full = bar_full + 8 * stage;
+          const uint32_t full = bar_fullA + 8 * stage;
           if (lane == 0) {
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            mbar_arrive_expect_tx(full, tx_bytes);
+            mbar_wait(bar_emptyA + 8 * stage, phase ^ 1);
+            mbar_arrive_expect_tx(full, 2u * row_bytes);
           }
           __syncwarp();
-          if (bytes) bulk_g2s(smem_base + stage * stage_bytes + dst_off, src, bytes, full);
+          if (lane < 2) bulk_g2s(smem_base + stage * a_bytes + (uint32_t)lane * row_bytes, src, row_bytes, full);
           src += src_step;
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == AS) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ================================ weight producer: slots of up to CONV_BT taps (12 KB), one bulk copy each
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        const int ntile = w % p.ntiles_n;
+        for (int s = 0; s < p.nseg; ++s) {
+          const ConvSeg& sg = p.seg[s];
+          const char* src = reinterpret_cast<const char*>(sg.wpack + (long long)ntile * sg.ksteps * sg.ntaps * (CONV_B_TAP / 2));
+          for (int ks = 0; ks < sg.ksteps; ++ks) {
+            for (int t0 = 0; t0 < sg.ntaps; t0 += CONV_BT) {
+              const uint32_t bytes = (uint32_t)min(CONV_BT, sg.ntaps - t0) * CONV_B_TAP;
+              mbar_wait(bar_emptyB + 8 * stage, phase ^ 1);
+              mbar_arrive_expect_tx(bar_fullB + 8 * stage, bytes);
+              bulk_g2s(bring_base + stage * CONV_B_SLOT, src, bytes, bar_fullB + 8 * stage);
+              src += bytes;
+              if (++stage == BS) { stage = 0; phase ^= 1; }
+            }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer. The warp runs convergently (all operands live in uniform registers);
-    // one elected lane issues. Taps outer, tiles inner: consecutive MMAs share the B descriptor and advance A / D by one tile.
-    constexpr uint32_t idesc = make_idesc_bf16(CONV_TM, CONV_NT);
-    constexpr uint32_t bdesc_lo_hi = ((CONV_NT / 8) * 128 >> 4) << 16;   // LBO of B
+    // one elected lane issues. Per tap: weights (A, M = 128 cout) x pixel window (B, N = 256 then the remaining pixels).
+    constexpr uint32_t idesc256 = make_idesc_bf16(CONV_NT, 256);
+    constexpr uint32_t wdesc_lo_hi = ((CONV_NT / 8) * 128 >> 4) << 16;       // LBO of the weight blocks
     constexpr uint64_t desc_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, descriptor version 1
-    int stage = 0;
-    uint32_t phase = 0;
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
     int item = 0;
-    const uint32_t b_off16 = (uint32_t)p.a_stage >> 4;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++item) {
       const WorkItem wi = decode_work(p, w);
       const int acc = item % ACC;
-      const uint32_t d0 = tmem_base + (uint32_t)acc * (MAXG * CONV_NT);
+      const uint32_t d0 = tmem_base + (uint32_t)acc * (MAXG * CONV_TM);
+      // pixel groups: [0, n0) with one MMA of N = n0 (<= 256) and, if the item has more than two tiles, [256, 256 + n1)
+      const int n0 = min(wi.G, 2) * CONV_TM, n1 = (wi.G - 2) * CONV_TM;
+      const uint32_t idesc0 = (n0 == 256) ? idesc256 : make_idesc_bf16(CONV_NT, CONV_TM);
+      const uint32_t idesc1 = (n1 == 256) ? idesc256 : make_idesc_bf16(CONV_NT, CONV_TM);
       mbar_wait_warp(bar_tempty + 8 * acc, (((uint32_t)(item / ACC)) & 1) ^ 1);  // epilogue drained this accumulator
       tc_fence_after();
       uint32_t fresh = 1;  // first k-step of the item overwrites the accumulators
       for (int s = 0; s < p.nseg; ++s) {
         const ConvSeg& sg = p.seg[s];
         const int npix = wi.G * CONV_TM + (sg.ht + sg.hb) * p.Wp + sg.hl + sg.hr;
-        const uint32_t adesc_lo_hi = ((uint32_t)npix & 0x3FFF) << 16;  // LBO of A = npix * 16 B
+        const uint32_t xdesc_lo_hi = ((uint32_t)npix & 0x3FFF) << 16;  // LBO of the pixel windows = npix * 16 B
         const int ntaps = sg.ntaps;
         for (int ks = 0; ks < sg.ksteps; ++ks) {
-          mbar_wait_warp(bar_ready + 8 * stage, phase);   // strips landed and (if asked) normalised in place
-          tc_fence_after();
-          const uint32_t base16 = (smem_base + stage * stage_bytes) >> 4;
-          if (elect_one()) {
-            for (int t = 0; t < ntaps; ++t) {
-              const uint32_t a_lo = (base16 + (uint32_t)sg.aoff[t]) | adesc_lo_hi;
-              const uint64_t bdesc = desc_hi | (uint64_t)((base16 + b_off16 + (uint32_t)t * (CONV_B_TAP >> 4)) | bdesc_lo_hi);
-              const uint32_t accum = (fresh && t == 0) ? 0u : 1u;
-#pragma unroll
-              for (int i = 0; i < MAXG; ++i) {
-                if (i < wi.G)
-                  umma_bf16(d0 + i * CONV_NT, desc_hi | (uint64_t)(a_lo + i * (CONV_TM * 16 >> 4)), bdesc, idesc, accum);
+          mbar_wait_warp(bar_readyA + 8 * sa, pa);   // windows landed and (if asked) normalised in place
+          const uint32_t abase16 = (smem_base + sa * a_bytes) >> 4;
+          for (int t0 = 0; t0 < ntaps; t0 += CONV_BT) {
+            mbar_wait_warp(bar_fullB + 8 * sb, pb);  // this slot's taps landed
+            tc_fence_after();
+            const uint32_t bbase16 = (bring_base + sb * CONV_B_SLOT) >> 4;
+            const int nt = min(CONV_BT, ntaps - t0);
+            if (elect_one()) {
+              for (int t = 0; t < nt; ++t) {
+                const uint64_t wdesc = desc_hi | (uint64_t)((bbase16 + (uint32_t)t * (CONV_B_TAP >> 4)) | wdesc_lo_hi);
+                const uint32_t x_lo = (abase16 + (uint32_t)sg.aoff[t0 + t]) | xdesc_lo_hi;
+                const uint32_t accum = (fresh && t0 + t == 0) ? 0u : 1u;
+                if (n1 > 0) {  // two pixel groups share the weights: latch them in the A collector
+                  umma_bf16_afill(d0, wdesc, desc_hi | (uint64_t)x_lo, idesc0, accum);
+                  umma_bf16_alast(d0 + 256, wdesc, desc_hi | (uint64_t)(x_lo + (256 * 16 >> 4)), idesc1, accum);
+                } else {
+                  umma_bf16(d0, wdesc, desc_hi | (uint64_t)x_lo, idesc0, accum);
+                }
               }
             }
+            __syncwarp();
+            umma_commit_elect(bar_emptyB + 8 * sb);  // frees the weight slot when these MMAs retire
+            if (++sb == BS) { sb = 0; pb ^= 1; }
           }
-          __syncwarp();
           fresh = 0;
-          umma_commit_elect(bar_empty + 8 * stage);  // frees the stage when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          umma_commit_elect(bar_emptyA + 8 * sa);    // frees the activation slot
+          if (++sa == AS) { sa = 0; pa ^= 1; }
         }
       }
       umma_commit_elect(bar_tfull + 8 * acc);
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ================================ epilogue: TMEM -> regs -> (+bias,+temb) -> stats, bf16 store
-    const int q = warp & 3;                  // TMEM lane quarter this warp may read
-    const int et = threadIdx.x - 128;        // 0..127
+  } else if ((warp >= 4 && warp < 8) || warp >= 12) {
+    // ================================ epilogue (8 warps). TMEM lane = output channel, column = pixel. Two warps share a
+    // TMEM lane quarter and take alternate 32-pixel chunks.
+    const int q = warp & 3;                  // TMEM lane quarter = channels [32q, 32q + 32) of this cout tile
+    const int half = warp >> 3;              // 0: warps 4-7 (even chunks), 1: warps 12-15 (odd chunks)
+    uint8_t* tile = ttile + (half * 4 + q) * CONV_TTILE;
     const long long out_img_stride = (long long)(p.cout >> 3) * p.PL * 8;
     const int hw_end = p.H * p.Wp;
     const bool do_stats = p.stats != nullptr;
@@ -198,97 +235,75 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++item) {
       const WorkItem wi = decode_work(p, w);
       const int acc = item % ACC;
-      const uint32_t acc_col = (uint32_t)acc * (MAXG * CONV_NT);
-      {  // per-item additive vector: bias + timestep-embedding projection of this sample
-        const int c = wi.ntile * CONV_NT + et;
-        float b = p.bias ? p.bias[c] : 0.f;
-        if (p.temb) b += p.temb[(long long)wi.n * p.temb_stride + c];
-        asm volatile("bar.sync 1, 128;");   // previous item's readers are done with sbias
-        sbias[et] = b;
-        asm volatile("bar.sync 1, 128;");
-      }
-      __nv_bfloat16* out_img = p.out + (long long)wi.n * out_img_stride;
-      const long long plane0 = (long long)wi.ntile * 16 * p.PL * 8;
+      const uint32_t acc_col = (uint32_t)acc * (MAXG * CONV_TM);
+      const int c = wi.ntile * CONV_NT + q * 32 + lane;   // this thread's output channel
+      float bias = p.bias ? __ldg(p.bias + c) : 0.f;
+      if (p.temb) bias += __ldg(p.temb + (long long)wi.n * p.temb_stride + c);
+      // the four 8-channel planes this warp writes; each lane stores one pixel (16 B) per plane per 32-pixel chunk
+      __nv_bfloat16* out_pl = p.out + (long long)wi.n * out_img_stride + (long long)(wi.ntile * 16 + q * 4) * p.PL * 8;
 
       mbar_wait(bar_tfull + 8 * acc, ((uint32_t)(item / ACC)) & 1);
       tc_fence_after();
 
-      float st[4][16];
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int k = 0; k < 16; ++k) st[j][k] = 0.f;
-
-      const int G = (p.dbg & 8) ? 0 : wi.G;
-      for (int i = 0; i < G; ++i) {
-        const int m = wi.m0 + i * CONV_TM + q * 32 + lane;
-        const bool valid = (m < hw_end) && ((m % p.Wp) != p.W);
-        const long long pix = (long long)(p.lead + m) * 8;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(i * CONV_NT + j * 32), r);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]) + sbias[j * 32 + e];
-          if (valid) {
-#pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
-              uint4 o;
-              o.x = pack_bf16x2(v[c8 * 8 + 0], v[c8 * 8 + 1]);
-              o.y = pack_bf16x2(v[c8 * 8 + 2], v[c8 * 8 + 3]);
-              o.z = pack_bf16x2(v[c8 * 8 + 4], v[c8 * 8 + 5]);
-              o.w = pack_bf16x2(v[c8 * 8 + 6], v[c8 * 8 + 7]);
-              *reinterpret_cast<uint4*>(out_img + plane0 + (long long)(j * 4 + c8) * p.PL * 8 + pix) = o;
-            }
-            if (do_stats) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const float a = v[4 * k], b = v[4 * k + 1], c = v[4 * k + 2], d = v[4 * k + 3];
-                st[j][k] += (a + b) + (c + d);
-                st[j][8 + k] += (a * a + b * b) + (c * c + d * d);
-              }
+      float ssum = 0.f, ssq = 0.f;
+      const int nchunk = (p.dbg & 8) ? 0 : wi.G * (CONV_TM / 32);
+      for (int jc = half; jc < nchunk; jc += 2) {
+        const int mc = wi.m0 + jc * 32;
+        // validity mask of the chunk's 32 pixels (pad columns and the run-off behind the image are not stored / counted)
+        uint32_t mask;
+        {
+          const int nvalid = min(32, max(0, hw_end - mc));
+          mask = (nvalid == 32) ? 0xffffffffu : ((1u << nvalid) - 1u);
+          int cc = mc % p.Wp;
+          if (p.Wp > 32) {            // at most one pad column per chunk
+            const int pe = p.W - cc;
+            if (pe >= 0 && pe < 32) mask &= ~(1u << pe);
+          } else {
+            for (int e = 0; e < 32; ++e) {
+              if (cc == p.W) mask &= ~(1u << e);
+              if (++cc == p.Wp) cc = 0;
             }
           }
         }
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(jc * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float v = __uint_as_float(r[e]) + bias;
+          if (do_stats && ((mask >> e) & 1)) { ssum += v; ssq = fmaf(v, v, ssq); }
+          *reinterpret_cast<__nv_bfloat16*>(tile + e * CONV_TROW + lane * 2) = __float2bfloat16_rn(v);
+        }
+        __syncwarp();
+        if ((mask >> lane) & 1) {
+          const long long pix = (long long)(p.lead + mc + lane) * 8;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint4 o = *reinterpret_cast<const uint4*>(tile + lane * CONV_TROW + g * 16);
+            *reinterpret_cast<uint4*>(out_pl + (long long)g * p.PL * 8 + pix) = o;
+          }
+        }
+        __syncwarp();
       }
       // accumulators are drained: the MMA warp may reuse this TMEM stage
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc);
 
-      if (do_stats) {
-        // warp transpose-reduce: 16 values per 32-column chunk -> one lane per value, fp64 atomics
-        stat_t* sdst = p.stats + ((long long)wi.n * (p.cout >> 2) + wi.ntile * 32) * 2;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float v16[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) v16[k] = st[j][k];
-#pragma unroll
-          for (int half = 8, sh = 16; half >= 1; half >>= 1, sh >>= 1) {
-            const bool upper = (lane & sh) != 0;
-#pragma unroll
-            for (int k = 0; k < half; ++k) {
-              const float lo = v16[k], hi = v16[k + half];
-              const float send = upper ? lo : hi;
-              const float keep = upper ? hi : lo;
-              v16[k] = keep + __shfl_xor_sync(0xffffffffu, send, sh);
-            }
-          }
-          float tot = v16[0] + __shfl_xor_sync(0xffffffffu, v16[0], 1);
-          if ((lane & 1) == 0) {
-            const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            const int is_sq = idx >> 3, quad = idx & 7;
-            atomicAdd(sdst + (j * 8 + quad) * 2 + is_sq, (stat_t)tot);
-          }
+      if (do_stats) {  // quad (4-channel) partial sums: combine 4 neighbouring lanes, fp64 atomics
+        ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
+        ssq += __shfl_xor_sync(0xffffffffu, ssq, 1);
+        ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
+        ssq += __shfl_xor_sync(0xffffffffu, ssq, 2);
+        if ((lane & 3) == 0) {
+          stat_t* sdst = p.stats + ((long long)wi.n * (p.cout >> 2) + (c >> 2)) * 2;
+          atomicAdd(sdst, (stat_t)ssum);
+          atomicAdd(sdst + 1, (stat_t)ssq);
         }
       }
     }
   } else {
-    // ================================ transform warps (2, 3, 8..11): GroupNorm(+SiLU) of the landed strips, in place
-    const int tt = ((warp < 4) ? (warp - 2) : (warp - 6)) * 32 + lane;  // 0..191
-    const int hw_end = p.H * p.Wp;
+    // ================================ transform warps (2, 8..11): GroupNorm(+SiLU) of the landed windows, in place
+    const int tt = ((warp == 2) ? 0 : (warp - 7)) * 32 + lane;  // 0..159
     int stage = 0;
     uint32_t phase = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
@@ -297,10 +312,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
         const ConvSeg& sg = p.seg[s];
         const int npix = wi.G * CONV_TM + (sg.ht + sg.hb) * p.Wp + sg.hl + sg.hr;
         const float2* ssn = sg.ss ? sg.ss + (long long)wi.n * sg.ss_stride : nullptr;
-        // flat position of this thread's first pixel; (row, col) advance incrementally (128 pixels per step)
+        // flat position of this thread's first pixel; (row, col) advance incrementally (CONV_XF_THREADS pixels per step)
         const int m_first = wi.m0 - sg.ht * p.Wp - sg.hl + tt;
-        int row0 = (m_first >= 0) ? m_first / p.Wp : -1 - ((-1 - m_first) / p.Wp);  // floor division
-        int col0 = m_first - row0 * p.Wp;
+        const int row0 = (m_first >= 0) ? m_first / p.Wp : -1 - ((-1 - m_first) / p.Wp);  // floor division
+        const int col0 = m_first - row0 * p.Wp;
         const int drow = CONV_XF_THREADS / p.Wp, dcol = CONV_XF_THREADS - drow * p.Wp;
         const bool silu = sg.silu != 0;
         for (int ks = 0; ks < sg.ksteps; ++ks) {
@@ -315,9 +330,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
               ss1[2 * e] = make_float2(b.x * hs, b.y * hs); ss1[2 * e + 1] = make_float2(b.z * hs, b.w * hs);
             }
           }
-          mbar_wait(bar_full + 8 * stage, phase);
+          mbar_wait(bar_fullA + 8 * stage, phase);
           if (ssn && !(p.dbg & 64)) {
-            uint4* base = reinterpret_cast<uint4*>(smem + stage * stage_bytes);
+            uint4* base = reinterpret_cast<uint4*>(smem + stage * a_bytes);
             int row = row0, col = col0;
             for (int px = tt; px < npix; px += CONV_XF_THREADS) {
               const bool valid = (row >= 0) && (row < p.H) && (col < p.W);
@@ -325,7 +340,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
               if (valid) {
                 a = base[px];
                 b = base[npix + px];
-                if (silu && !(p.dbg & 256)) { a = xform_vec<true>(a, ss0); b = xform_vec<true>(b, ss1); }
+                if (silu) { a = xform_vec<true>(a, ss0); b = xform_vec<true>(b, ss1); }
                 else      { a = xform_vec<false>(a, ss0); b = xform_vec<false>(b, ss1); }
               }
               base[px] = a;
@@ -333,14 +348,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
               row += drow; col += dcol;
               if (col >= p.Wp) { col -= p.Wp; ++row; }
             }
-            if (!(p.dbg & 128)) fence_proxy_async_smem();
+            fence_proxy_async_smem();
           }
-          mbar_arrive(bar_ready + 8 * stage);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          mbar_arrive(bar_readyA + 8 * stage);
+          if (++stage == AS) { stage = 0; phase ^= 1; }
         }
       }
     }
-    (void)hw_end;
   }
 
   tc_fence_before();
@@ -351,7 +365,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
 template <int CFG>
 static cudaError_t launch_cfg(const ConvParams& p, int grid, size_t smem, cudaStream_t stream) {
   constexpr ConvCfg c = CONV_CFGS[CFG];
-  auto kern = conv_tc_kernel<c.maxg, c.acc, c.stages>;
+  auto kern = conv_tc_kernel<c.maxg, c.acc, c.astages, c.bstages>;
   static size_t attr = 0;
   if (smem > attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -368,7 +382,7 @@ cudaError_t launch_conv_tc(const ConvParams& p_in, int num_sms, cudaStream_t str
     const char* e = getenv("B200AD_CONV_DBG");
     dbg = e ? atoi(e) : 0;
     const char* c = getenv("B200AD_CONV_CFG");
-    cfg_env = c ? atoi(c) : 0;  // measured: with the GroupNorm transform fused, cfg 0 (less halo per MMA) wins
+    cfg_env = c ? atoi(c) : 0;
     if (cfg_env < 0 || cfg_env > 1) cfg_env = 0;
   }
   ConvParams p = p_in;
@@ -378,7 +392,7 @@ cudaError_t launch_conv_tc(const ConvParams& p_in, int num_sms, cudaStream_t str
   p.groups_per_img = (p.H * p.Wp + cfg.maxg * CONV_TM - 1) / (cfg.maxg * CONV_TM);
   p.ntiles_n = p.cout / CONV_NT;
   p.total_work = p.N * p.groups_per_img * p.ntiles_n;
-  // the two A windows of one k-step must fit the stage buffer
+  // the two windows of one k-step must fit an activation slot
   int a_stage = 0;
   for (int s = 0; s < p.nseg; ++s) {
     const ConvSeg& sg = p.seg[s];
@@ -388,7 +402,7 @@ cudaError_t launch_conv_tc(const ConvParams& p_in, int num_sms, cudaStream_t str
     for (int t = 0; t < sg.ntaps; ++t) p.seg[s].aoff[t] = (sg.dh[t] + sg.ht) * p.Wp + sg.dw[t] + sg.hl;
   }
   p.a_stage = (a_stage + 255) & ~255;
-  const size_t smem = (size_t)cfg.stages * (p.a_stage + CONV_B_STAGE) + 1024;
+  const size_t smem = (size_t)cfg.astages * p.a_stage + (size_t)cfg.bstages * CONV_B_SLOT + 8 * CONV_TTILE + 1024;
   if (smem > (size_t)CONV_SMEM_MAX) return cudaErrorInvalidValue;  // image too wide for this tiling
   const int grid = p.total_work < num_sms ? p.total_work : num_sms;
   if (grid <= 0) return cudaSuccess;

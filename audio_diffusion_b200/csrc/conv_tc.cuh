@@ -15,8 +15,13 @@ constexpr int CONV_SMEM_MAX = 227 * 1024;
 // Kernel configurations (compile-time): pixel tiles per work item, TMEM accumulator stages, smem ring depth.
 //   cfg 0: 4 tiles, 1 accumulator stage  (4 x 128 columns = all of TMEM; weights reused by 4 tiles; epilogue exposed)
 //   cfg 1: 2 tiles, 2 accumulator stages (epilogue of item k overlaps the MMAs of item k+1; twice the weight traffic)
-struct ConvCfg { int maxg, acc, stages; };
-constexpr ConvCfg CONV_CFGS[2] = {{4, 1, 3}, {2, 2, 3}};
+// Shared memory holds two independent rings: `astages` activation slots (one 16-channel k-step each: two 8-channel
+// windows) and `bstages` weight slots of CONV_BT taps each, so weights (the bulk of the bytes) are prefetched at a finer
+// grain and the TMA -> transform -> MMA chain of the activations gets a deeper ring.
+struct ConvCfg { int maxg, acc, astages, bstages; };
+constexpr int CONV_BT = 3;                       // taps per weight slot
+constexpr int CONV_B_SLOT = CONV_BT * CONV_B_TAP;
+constexpr ConvCfg CONV_CFGS[2] = {{4, 1, 4, 6}, {2, 2, 4, 8}};
 
 // One K-segment: a source tensor (PF8) with its tap set and packed weights. A 3x3 conv is one
 // segment with 9 taps; a fused 1x1 shortcut adds one 1-tap segment per shortcut source; a stride-2

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const ConvOutParams p) {
         for (int e = 0; e < 4; ++e) {
           const float2 f = unpack_bf16x2(uu[e]);
           const int c = pl * 8 + 2 * e;
-          r[e] = pack_bf16x2(silu_f(f.x * scale[c] + shift[c]), silu_f(f.y * scale[c + 1] + shift[c + 1]));
+          r[e] = pack_bf16x2(silu_tanh(f.x * scale[c] + shift[c]), silu_tanh(f.y * scale[c + 1] + shift[c + 1]));
         }
         o = make_uint4(r[0], r[1], r[2], r[3]);
       }

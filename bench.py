@@ -114,6 +114,8 @@ def run_reference(args):
     rank, world, local = dist_env()
     if rank != 0:
         return
+    if torch.get_num_threads() == 1 and (os.cpu_count() or 1) > 2:
+        torch.set_num_threads(max(1, os.cpu_count() // 2))  # torchrun forces OMP_NUM_THREADS=1: use the physical cores
     cores = torch.get_num_threads()
     batch, hw = 1, 256
     steps = max(1, min(args.steps, 3))
