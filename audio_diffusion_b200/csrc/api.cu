@@ -25,14 +25,14 @@ struct ConvScratch {
 static ConvScratch conv_scratch_layout(int N, int cin, int cout, int H, int W, int K, int stride) {
   ConvScratch s{};
   const Geom gi = make_geom(N, H, W);
-  const int Ho = H / stride, Wo = W / stride;
+  const int Ho = stride > 0 ? H / stride : 2 * H, Wo = stride > 0 ? W / stride : 2 * W;
   const Geom go = make_geom(N, Ho, Wo);
   size_t off = 0;
   s.x = off; off = al(off + (size_t)N * (cin / 8) * gi.PL * 16);
   s.par = off; if (stride == 2) off = al(off + (size_t)4 * N * (cin / 8) * go.PL * 16);
   s.res = off; off = al(off + (size_t)N * (cout / 8) * go.PL * 16);
   s.out = off; off = al(off + (size_t)N * (cout / 8) * go.PL * 16);
-  s.wpack = off; off = al(off + (size_t)(cout / 128) * (cin / 16) * K * K * CONV_B_TAP);
+  s.wpack = off; off = al(off + (size_t)(cout / 128) * (cin / 16) * (K * K > 16 ? K * K : 16) * CONV_B_TAP);
   s.ident = off; off = al(off + (size_t)(cout / 128) * (cout / 16) * CONV_B_TAP);
   s.stats = off; off = al(off + (size_t)N * (cout / 4) * 2 * sizeof(stat_t));
   s.instats = off; off = al(off + (size_t)N * (cin / 4) * 2 * sizeof(stat_t));
@@ -50,7 +50,8 @@ static int conv2d_impl(const float* x, const float* w, const float* bias, const 
                        const float* gn_gamma, const float* gn_beta, int gn_groups, float gn_eps, int gn_silu,
                        void* scratch, size_t scratch_bytes, void* stream) {
   if (cin % 16 || cout % 128) return set_err("conv2d: cin %% 16 and cout %% 128 must be 0");
-  if (!((K == 3 || K == 1) && (stride == 1 || (stride == 2 && K == 3)))) return set_err("conv2d: unsupported K/stride");
+  if (!((K == 3 || K == 1) && (stride == 1 || ((stride == 2 || stride == -2) && K == 3)))) return set_err("conv2d: unsupported K/stride");
+  if (stride == -2 && (residual || gn_gamma || temb)) return set_err("conv2d: upsample form takes no residual / GroupNorm / temb");
   if (stride == 2 && (H % 2 || W % 2)) return set_err("conv2d: stride 2 needs even H, W");
   if (stride == 2 && (residual || gn_gamma)) return set_err("conv2d: residual / fused GroupNorm need stride 1");
   const ConvScratch L = conv_scratch_layout(N, cin, cout, H, W, K, stride);
@@ -58,7 +59,7 @@ static int conv2d_impl(const float* x, const float* w, const float* bias, const 
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* sb = (uint8_t*)scratch;
   CK(cudaMemsetAsync(sb, 0, L.total, st));
-  const int Ho = H / stride, Wo = W / stride;
+  const int Ho = stride > 0 ? H / stride : 2 * H, Wo = stride > 0 ? W / stride : 2 * W;
   const Geom go = make_geom(N, Ho, Wo);
   __nv_bfloat16* xp = (__nv_bfloat16*)(sb + L.x);
   __nv_bfloat16* par = (__nv_bfloat16*)(sb + L.par);
@@ -75,7 +76,9 @@ static int conv2d_impl(const float* x, const float* w, const float* bias, const 
   p.out = op; p.bias = bias; p.temb = temb; p.temb_stride = cout;
   p.stats = stats_out ? stp : nullptr;
   const long long img_stride = (long long)(cin / 8) * go.PL * 8;
-  if (stride == 1) {
+  if (stride == -2) {
+    // segments are built per output parity below
+  } else if (stride == 1) {
     PackTaps t{};
     t.ntaps = K * K;
     for (int k = 0; k < K * K; ++k) { t.kh[k] = k / K; t.kw[k] = k % K; }
@@ -128,7 +131,34 @@ static int conv2d_impl(const float* x, const float* w, const float* bias, const 
   int dev = 0, sms = 148;
   CK(cudaGetDevice(&dev));
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  CK(launch_conv_tc(p, sms, st));
+  if (stride == -2) {  // nearest-2x upsample + 3x3 conv as four folded 2x2 convs on the low-res input
+    const Geom gi = make_geom(N, H, W);
+    p.H = H; p.W = W; p.Wp = gi.Wp; p.lead = gi.lead; p.PL = gi.PL;
+    p.up2 = 1;
+    p.nseg = 1;
+    size_t woff = 0;
+    for (int pa = 0; pa < 2; ++pa)
+      for (int pb = 0; pb < 2; ++pb) {
+        const UpTaps ut = taps_up2(pa, pb);
+        __nv_bfloat16* wseg = wp + woff / 2;
+        CK(launch_pack_weights(w, cout, cin, 3, 3, 0, cin / 16, ut.pack, wseg, st));
+        woff += (size_t)(cout / 128) * (cin / 16) * 4 * CONV_B_TAP;
+        ConvSeg& s = p.seg[0];
+        s.src = xp; s.wpack = wseg; s.img_stride = (long long)(cin / 8) * gi.PL * 8; s.ksteps = cin / 16; s.ntaps = 4;
+        s.ht = s.hb = s.hl = s.hr = 0; s.ss = nullptr; s.ss_stride = 0; s.silu = 0;
+        for (int t = 0; t < 4; ++t) {
+          s.dh[t] = ut.dh[t]; s.dw[t] = ut.dw[t];
+          if (ut.dh[t] < 0) s.ht = 1;
+          if (ut.dh[t] > 0) s.hb = 1;
+          if (ut.dw[t] < 0) s.hl = 1;
+          if (ut.dw[t] > 0) s.hr = 1;
+        }
+        p.oy = pa; p.ox = pb;
+        CK(launch_conv_tc(p, sms, st));
+      }
+  } else {
+    CK(launch_conv_tc(p, sms, st));
+  }
   CK(launch_pf8_to_nchw(op, y, N, cout, Ho, Wo, st));
   if (stats_out) CK(launch_stats_to_float(stp, stats_out, N * (cout / 4) * 2, st));
   return 0;

@@ -228,7 +228,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
     const int q = warp & 3;                  // TMEM lane quarter = channels [32q, 32q + 32) of this cout tile
     const int half = warp >> 3;              // 0: warps 4-7 (even chunks), 1: warps 12-15 (odd chunks)
     uint8_t* tile = ttile + (half * 4 + q) * CONV_TTILE;
-    const long long out_img_stride = (long long)(p.cout >> 3) * p.PL * 8;
+    const Geom og = make_geom(p.N, p.up2 ? 2 * p.H : p.H, p.up2 ? 2 * p.W : p.W);   // geometry of the output tensor
+    const long long out_img_stride = (long long)(p.cout >> 3) * og.PL * 8;
     const int hw_end = p.H * p.Wp;
     const bool do_stats = p.stats != nullptr;
     int item = 0;
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
       float bias = p.bias ? __ldg(p.bias + c) : 0.f;
       if (p.temb) bias += __ldg(p.temb + (long long)wi.n * p.temb_stride + c);
       // the four 8-channel planes this warp writes; each lane stores one pixel (16 B) per plane per 32-pixel chunk
-      __nv_bfloat16* out_pl = p.out + (long long)wi.n * out_img_stride + (long long)(wi.ntile * 16 + q * 4) * p.PL * 8;
+      __nv_bfloat16* out_pl = p.out + (long long)wi.n * out_img_stride + (long long)(wi.ntile * 16 + q * 4) * og.PL * 8;
 
       mbar_wait(bar_tfull + 8 * acc, ((uint32_t)(item / ACC)) & 1);
       tc_fence_after();
@@ -276,11 +277,17 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
         }
         __syncwarp();
         if ((mask >> lane) & 1) {
-          const long long pix = (long long)(p.lead + mc + lane) * 8;
+          long long pix;
+          if (p.up2) {  // scatter into the 2x tensor at this launch's parity
+            const int m = mc + lane, hh = m / p.Wp, ww = m - hh * p.Wp;
+            pix = (long long)(og.lead + (2 * hh + p.oy) * og.Wp + 2 * ww + p.ox) * 8;
+          } else {
+            pix = (long long)(p.lead + mc + lane) * 8;
+          }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const uint4 o = *reinterpret_cast<const uint4*>(tile + lane * CONV_TROW + g * 16);
-            *reinterpret_cast<uint4*>(out_pl + (long long)g * p.PL * 8 + pix) = o;
+            *reinterpret_cast<uint4*>(out_pl + (long long)g * og.PL * 8 + pix) = o;
           }
         }
         __syncwarp();

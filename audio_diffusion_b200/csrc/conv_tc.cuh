@@ -58,6 +58,9 @@ struct ConvParams {
   const float* temb;            // optional per-sample additive term [N][temb_stride] (offset applied)
   int temb_stride;
   stat_t* stats;                // optional [N][cout/4][2] running (sum, sumsq) of the stored output
+  // Folded nearest-2x upsample: the item geometry (N, H, W, ...) is the LOW-res input; low-res pixel (h, w) is stored at
+  // (2h + oy, 2w + ox) of the (2H, 2W) output tensor. One launch per output parity (oy, ox) with pre-summed 2x2 weights.
+  int up2, oy, ox;
   int dbg;                      // B200AD_CONV_DBG bit flags (timing experiments only): 1 no stats, 2 no stores, 4 no tmem ld, 8 no epilogue
 };
 

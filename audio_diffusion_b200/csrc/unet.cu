@@ -297,7 +297,9 @@ static void build_packed_layout(b200ad_unet* h) {
     }
     if (i != nb - 1) {
       const std::string nm = S("up_blocks.%d.upsamplers.0.conv", i);
-      add_job(h, b, nm + "#0", nm + ".weight", out_c, out_c, 3, 0, out_c, taps_3x3());
+      for (int pa = 0; pa < 2; ++pa)
+        for (int pb = 0; pb < 2; ++pb)
+          add_job(h, b, nm + S("#p%d", pa * 2 + pb), nm + ".weight", out_c, out_c, 3, 0, out_c, taps_up2(pa, pb).pack);
     }
   }
   const int D = c.block_out_channels[0] * 4;
@@ -685,26 +687,34 @@ static int build_plan(b200ad_unet* h, uint8_t* ws_base, int N, int H, int W, siz
       }
       if (i != nb - 1) {
         const std::string nm = S("up_blocks.%d.upsamplers.0.conv", i);
-        Act up = B.pooled("upsampled", out_c, hh * 2, ww * 2, false);
-        {
-          Op op{};
-          op.kind = OP_UPSAMPLE;
-          op.src = x.p; op.dst = up.p; op.C = out_c; op.H = hh; op.W = ww;
-          plan.push_back(op);
-        }
+        // nearest-2x + 3x3 conv folded into four 2x2 convs on the low-res tensor (one launch per output parity)
+        Act y = B.pooled("up_conv", out_c, hh * 2, ww * 2, true);
+        for (int pa = 0; pa < 2; ++pa)
+          for (int pb = 0; pb < 2; ++pb) {
+            const UpTaps ut = taps_up2(pa, pb);
+            Op op{};
+            op.kind = OP_CONV;
+            ConvParams& p = op.conv;
+            Act lo = y;                       // item geometry = low-res input geometry, output tensor = y
+            lo.H = hh; lo.W = ww;
+            B.conv_common(p, lo);
+            p.up2 = 1; p.oy = pa; p.ox = pb;
+            p.nseg = 1;
+            ConvSeg& sgm = p.seg[0];
+            B.set_seg(sgm, x.p, out_c, hh, ww, B.WP(nm + S("#p%d", pa * 2 + pb)), ut.pack);
+            sgm.ht = sgm.hb = sgm.hl = sgm.hr = 0;
+            for (int t = 0; t < 4; ++t) {
+              sgm.dh[t] = ut.dh[t]; sgm.dw[t] = ut.dw[t];
+              if (ut.dh[t] < 0) sgm.ht = 1;
+              if (ut.dh[t] > 0) sgm.hb = 1;
+              if (ut.dw[t] < 0) sgm.hl = 1;
+              if (ut.dw[t] > 0) sgm.hr = 1;
+            }
+            p.bias = B.P(nm + ".bias");
+            p.temb = nullptr; p.temb_stride = 0;
+            plan.push_back(op);
+          }
         hh *= 2; ww *= 2;
-        Act y = B.pooled("up_conv", out_c, hh, ww, true);
-        {
-          Op op{};
-          op.kind = OP_CONV;
-          ConvParams& p = op.conv;
-          B.conv_common(p, y);
-          p.nseg = 1;
-          B.set_seg(p.seg[0], up.p, out_c, hh, ww, B.WP(nm + "#0"), taps_3x3());
-          p.bias = B.P(nm + ".bias");
-          p.temb = nullptr; p.temb_stride = 0;
-          plan.push_back(op);
-        }
         h->taps[nm] = y;
         x = y;
       }
@@ -860,7 +870,8 @@ extern "C" int b200ad_unet_profile_step(b200ad_unet* h, const float* x, const fl
     if (saved[i].kind == OP_CONV) {
       const ConvParams& p = saved[i].conv;
       double k = 0;
-      for (int s = 0; s < p.nseg; ++s) k += (double)p.seg[s].ntaps * p.seg[s].ksteps * 16;
+      // algorithmic taps: a folded upsample launch stands for the 3x3 conv on its quarter of the output pixels
+      for (int s = 0; s < p.nseg; ++s) k += (double)(p.up2 ? 9 : p.seg[s].ntaps) * p.seg[s].ksteps * 16;
       fl = 2.0 * p.N * p.H * p.W * p.cout * k;
     }
     op_flops[i] = fl;

@@ -145,3 +145,29 @@ def test_fused_groupnorm_conv(cuda, silu, N, cin, cout, H, W, K):
     torch.cuda.synchronize()
     err = (y.cpu() - ref).abs().max().item()
     assert err <= 2.5e-2 * ref.abs().max().item(), f"err {err} scale {ref.abs().max().item()}"
+
+
+@pytest.mark.parametrize("N,C,cout,H,W", [(2, 128, 128, 16, 16), (1, 128, 256, 8, 64), (1, 256, 128, 4, 128)])
+def test_upsample_conv_folded(cuda, N, C, cout, H, W):
+    """conv3x3(nearest_2x(x)) computed as four 2x2 convs with pre-summed weights on the low-res tensor (b200ad_conv2d with
+    stride = -2). The weight sums are rounded to bf16 once, so compare against the fp32 reference with 2e-2 * max|ref|."""
+    from audio_diffusion_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(21)
+    x = _bf(torch.randn(N, C, H, W, generator=g))
+    w = _bf(torch.randn(cout, C, 3, 3, generator=g) / (C * 9) ** 0.5)
+    b = torch.randn(cout, generator=g)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w, b, padding=1)
+    xd, wd, bd = x.to(cuda), w.to(cuda), b.to(cuda)
+    y = torch.empty(N, cout, 2 * H, 2 * W, device=cuda)
+    stats = torch.empty(N, cout // 4, 2, device=cuda)
+    nb = L.b200ad_conv2d_scratch_bytes(N, C, cout, H, W, 3, -2)
+    scratch = torch.empty(nb, dtype=torch.uint8, device=cuda)
+    _lib.check(L.b200ad_conv2d(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), None, None, y.data_ptr(), stats.data_ptr(),
+                               N, C, cout, H, W, 3, -2, scratch.data_ptr(), nb, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    err = (y.cpu() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item(), err
+    q = ref.view(N, cout // 4, 4, 4 * H * W)
+    s_ref = torch.stack([q.sum(dim=(2, 3)), (q * q).sum(dim=(2, 3))], dim=-1)
+    assert (stats.cpu() - s_ref).abs().max().item() <= 3e-2 * s_ref[..., 1].abs().max().item() + 1e-3 * 4 * H * W
