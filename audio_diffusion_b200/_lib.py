@@ -23,6 +23,14 @@ class UNetConfigC(C.Structure):
     ]
 
 
+class VAEConfigC(C.Structure):
+    _fields_ = [
+        ("in_channels", C.c_int), ("out_channels", C.c_int), ("latent_channels", C.c_int), ("layers_per_block", C.c_int),
+        ("num_blocks", C.c_int), ("block_out_channels", C.c_int * MAX_BLOCKS), ("norm_num_groups", C.c_int),
+        ("norm_eps", C.c_float),
+    ]
+
+
 class StepCoefC(C.Structure):
     _fields_ = [("sqrt_1m_at", C.c_float), ("inv_sqrt_at", C.c_float), ("clip", C.c_float), ("c_x0", C.c_float),
                 ("c_xt", C.c_float), ("c_eps", C.c_float), ("c_z", C.c_float), ("do_clip", C.c_int)]
@@ -53,6 +61,19 @@ SYMBOLS = {
                                       C.POINTER(_I), C.POINTER(C.c_double), _I, _VP]),
     "b200ad_unet_debug_tensor": (_I, [_VP, C.c_char_p, _VP, C.POINTER(_I), _VP]),
     "b200ad_unet_last_launch_count": (_I, [_VP]),
+    "b200ad_vae_create": (_I, [C.POINTER(VAEConfigC), C.POINTER(_VP)]),
+    "b200ad_vae_destroy": (None, [_VP]),
+    "b200ad_vae_num_params": (_I, [_VP]),
+    "b200ad_vae_param_name": (C.c_char_p, [_VP, _I]),
+    "b200ad_vae_param_shape": (_I, [_VP, _I, C.POINTER(C.c_int64)]),
+    "b200ad_vae_packed_bytes": (_SZ, [_VP]),
+    "b200ad_vae_workspace_bytes": (_SZ, [_VP, _I, _I, _I]),
+    "b200ad_vae_set_params": (_I, [_VP, C.POINTER(_VP), _VP, _SZ, _VP]),
+    "b200ad_vae_bind_workspace": (_I, [_VP, _VP, _SZ, _I, _I, _I, _VP]),
+    "b200ad_vae_encode": (_I, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    "b200ad_vae_decode": (_I, [_VP, _VP, _VP, _VP]),
+    "b200ad_vae_debug_tensor": (_I, [_VP, C.c_char_p, _VP, C.POINTER(_I), _VP]),
+    "b200ad_vae_last_launch_count": (_I, [_VP]),
     "b200ad_conv2d_scratch_bytes": (_SZ, [_I] * 7),
     "b200ad_conv2d": (_I, [_VP] * 7 + [_I] * 7 + [_VP, _SZ, _VP]),
     "b200ad_gn_conv2d": (_I, [_VP, _VP, _VP, _I, C.c_float, _I, _VP, _VP, _VP] + [_I] * 6 + [_VP, _SZ, _VP]),

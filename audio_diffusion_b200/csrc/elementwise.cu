@@ -9,7 +9,7 @@ namespace b200ad {
 
 // ------------------------------------------------------------------------------------ weight packing
 __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin_total, int KH, int KW, int cin_off,
-                                    int ksteps, PackTaps taps, __nv_bfloat16* __restrict__ dst, long long nvec) {
+                                    int ksteps, PackTaps taps, __nv_bfloat16* __restrict__ dst, long long nvec, int cout_real) {
   const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= nvec) return;
   const int r = (int)(id & 7);
@@ -27,7 +27,9 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int c
   for (int kk = 0; kk < 8; ++kk) {
     const float* wp = w + ((long long)co * cin_total + ci0 + kk) * KH * KW;
     float a = 0.f;
-    if (taps.fold) {
+    if (co >= cout_real) {
+      // rows beyond the real output channels (cout padded to the 128-channel tile) are zero
+    } else if (taps.fold) {
       const unsigned mask = taps.fold_mask[tap];
       for (int t = 0; t < KH * KW; ++t)
         if (mask & (1u << t)) a += wp[t];
@@ -43,11 +45,12 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int c
 }
 
 cudaError_t launch_pack_weights(const float* w, int cout, int cin_total, int KH, int KW, int cin_off, int ksteps,
-                                const PackTaps& taps, __nv_bfloat16* dst, cudaStream_t s) {
+                                const PackTaps& taps, __nv_bfloat16* dst, cudaStream_t s, int cout_real) {
   const long long nvec = (long long)(cout / 128) * ksteps * taps.ntaps * 256;
   const int threads = 256;
   const long long blocks = (nvec + threads - 1) / threads;
-  pack_weights_kernel<<<(unsigned)blocks, threads, 0, s>>>(w, cout, cin_total, KH, KW, cin_off, ksteps, taps, dst, nvec);
+  pack_weights_kernel<<<(unsigned)blocks, threads, 0, s>>>(w, cout, cin_total, KH, KW, cin_off, ksteps, taps, dst, nvec,
+                                                             cout_real < 0 ? cout : cout_real);
   return cudaGetLastError();
 }
 

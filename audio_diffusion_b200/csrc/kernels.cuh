@@ -15,7 +15,7 @@ struct PackTaps {
   int fold;
 };
 cudaError_t launch_pack_weights(const float* w, int cout, int cin_total, int KH, int KW, int cin_off, int ksteps,
-                                const PackTaps& taps, __nv_bfloat16* dst, cudaStream_t s);
+                                const PackTaps& taps, __nv_bfloat16* dst, cudaStream_t s, int cout_real = -1);
 
 // nearest-2x upsample + 3x3 conv, output parity (a, b): a 2x2 conv on the low-res input whose taps are sums of the 3x3
 // taps that read the same low-res pixel. Row taps: a = 0 -> dh = -1 (kh 0), dh = 0 (kh 1,2); a = 1 -> dh = 0 (kh 0,1), +1 (kh 2).
@@ -108,5 +108,13 @@ cudaError_t launch_temb(const float* t, int N, int dim0, const float* w1, const 
 
 // self-attention core on the fused qkv tensor (PF8, 3*C channels: q | k | v; head_dim 8 = one plane per head).
 cudaError_t launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int N, int C, int H, int W, cudaStream_t s);
+
+// generic single-head attention over the fused qkv tensor (AutoencoderKL mid block); scores: N * seq * seq floats of scratch
+cudaError_t launch_attention_1head(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* scores, int N, int C, int H, int W,
+                                   cudaStream_t s);
+// quant_conv + DiagonalGaussianDistribution.sample on the encoder output; post_quant_conv (1x1 on fp32 NCHW latents)
+cudaError_t launch_vae_sample(const __nv_bfloat16* enc, const float* wq, const float* bq, const float* noise, float* z,
+                              float* moments, int N, int C, int L, int H, int W, cudaStream_t s);
+cudaError_t launch_mix1x1(const float* x, const float* w, const float* b, float* y, int N, int L, int HW, cudaStream_t s);
 
 }  // namespace b200ad

@@ -156,3 +156,207 @@ cudaError_t launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int N
 }
 
 }  // namespace b200ad
+
+// =====================================================================================================================
+// Generic single-head attention (AutoencoderKL mid block: one head of dim C = 512 over seq = H*W up to 1024+).
+// Runs once per sample (not per denoising step), so three plain tiled SIMT kernels: scores, row softmax, P*V.
+// Reference semantics: diffusers Attention (AttnProcessor2_0) with heads = 1 — oracle/vae_oracle.py::_attn.
+namespace b200ad {
+
+__device__ __forceinline__ long long pf8_pix(const Geom& g, int p, int W) {
+  return (long long)(g.lead + (p / W) * g.Wp + (p % W)) * 8;
+}
+
+// S[n][q][k] = scale * sum_c Q[q][c] K[k][c];  qkv: PF8 with 3C channels (q | k | v).  grid (seq/64, seq/64, N), 256 thr
+__global__ void __launch_bounds__(256) attn_scores_kernel(const __nv_bfloat16* __restrict__ qkv, float* __restrict__ S,
+                                                          int N, int C, int H, int W, float scale) {
+  __shared__ float qs[16][65], ks[16][65];
+  const Geom g = make_geom(N, H, W);
+  const int seq = H * W, planes = C >> 3;
+  const int n = blockIdx.z, q0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+  const __nv_bfloat16* base = qkv + (long long)n * 3 * planes * g.PL * 8;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int c0 = 0; c0 < C; c0 += 16) {
+    // 64 pixels x 16 channels each for Q and K: 128 (pixel, plane) vectors apiece
+    for (int i = threadIdx.x; i < 256; i += 256) {
+      const int which = i >> 7, r = i & 127, px = r & 63, pl = r >> 6;
+      const int p = (which ? k0 : q0) + px;
+      float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (p < seq) {
+        const int plane = (which ? planes : 0) + (c0 >> 3) + pl;
+        const uint4 u = *reinterpret_cast<const uint4*>(base + (long long)plane * g.PL * 8 + pf8_pix(g, p, W));
+        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = unpack_bf16x2(uu[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+      }
+      float (*dst)[65] = which ? ks : qs;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dst[pl * 8 + e][px] = v[e];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = qs[c][ty + 16 * i]; b[i] = ks[c][tx + 16 * i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int q = q0 + ty + 16 * i, k = k0 + tx + 16 * j;
+      if (q < seq && k < seq) S[((long long)n * seq + q) * seq + k] = acc[i][j] * scale;
+    }
+}
+
+// in-place softmax over rows of length seq. grid (seq, N), 256 threads
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ S, int seq) {
+  __shared__ float red[8];
+  float* row = S + ((long long)blockIdx.y * seq + blockIdx.x) * seq;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < seq; i += blockDim.x) mx = fmaxf(mx, row[i]);
+  for (int sh = 16; sh >= 1; sh >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, sh));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < seq; i += blockDim.x) { const float e = __expf(row[i] - mx); row[i] = e; s += e; }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int i = 0; i < 8; ++i) s += red[i];
+  const float inv = 1.0f / s;
+  for (int i = threadIdx.x; i < seq; i += blockDim.x) row[i] *= inv;
+}
+
+// O[q][c] = sum_k P[q][k] V[k][c] -> PF8 bf16 (C channels). grid (seq/64, C/64, N), 256 threads
+__global__ void __launch_bounds__(256) attn_pv_kernel(const float* __restrict__ P, const __nv_bfloat16* __restrict__ qkv,
+                                                      __nv_bfloat16* __restrict__ out, int N, int C, int H, int W) {
+  __shared__ float ps[16][65], vs[16][65];
+  const Geom g = make_geom(N, H, W);
+  const int seq = H * W, planes = C >> 3;
+  const int n = blockIdx.z, q0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const __nv_bfloat16* vbase = qkv + ((long long)n * 3 * planes + 2 * planes) * g.PL * 8;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // tx -> channel, ty -> query
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < seq; k0 += 16) {
+    for (int i = threadIdx.x; i < 1024; i += 256) {   // P tile: 64 q x 16 k
+      const int kk = i & 15, qq = i >> 4;
+      const int q = q0 + qq, k = k0 + kk;
+      ps[kk][qq] = (q < seq && k < seq) ? P[((long long)n * seq + q) * seq + k] : 0.f;
+    }
+    if (threadIdx.x < 128) {                            // V tile: 16 k x 64 c = 16 x 8 vectors
+      const int kk = threadIdx.x & 15, pl = threadIdx.x >> 4;
+      const int k = k0 + kk;
+      float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (k < seq) {
+        const uint4 u = *reinterpret_cast<const uint4*>(vbase + (long long)((c0 >> 3) + pl) * g.PL * 8 + pf8_pix(g, k, W));
+        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 f = unpack_bf16x2(uu[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) vs[kk][pl * 8 + e] = v[e];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = ps[k][ty * 4 + i]; b[i] = vs[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  // thread holds queries ty*4..+3, channels c0 + tx*4..+3 (half of an 8-channel vector)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = q0 + ty * 4 + i;
+    if (q >= seq) continue;
+    const int c = c0 + tx * 4;
+    __nv_bfloat16* dp = out + ((long long)n * planes + (c >> 3)) * g.PL * 8 + pf8_pix(g, q, W) + (c & 7);
+    uint2 o;
+    o.x = pack_bf16x2(acc[i][0], acc[i][1]);
+    o.y = pack_bf16x2(acc[i][2], acc[i][3]);
+    *reinterpret_cast<uint2*>(dp) = o;
+  }
+}
+
+cudaError_t launch_attention_1head(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* scores, int N, int C, int H, int W,
+                                   cudaStream_t s) {
+  const int seq = H * W;
+  const int t = (seq + 63) / 64;
+  attn_scores_kernel<<<dim3(t, t, N), 256, 0, s>>>(qkv, scores, N, C, H, W, rsqrtf((float)C));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  softmax_rows_kernel<<<dim3(seq, N), 256, 0, s>>>(scores, seq);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  attn_pv_kernel<<<dim3(t, C / 64, N), 256, 0, s>>>(scores, qkv, out, N, C, H, W);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// AutoencoderKL.encode tail: quant_conv (1x1, 2L -> 2L) on the encoder output (PF8, first 2L channels of plane 0) and
+// DiagonalGaussianDistribution.sample(): z = mean + exp(0.5 * clamp(logvar, -30, 20)) * noise  -> fp32 NCHW (N, L, H, W).
+__global__ void vae_sample_kernel(const __nv_bfloat16* __restrict__ enc, const float* __restrict__ wq, const float* __restrict__ bq,
+                                  const float* __restrict__ noise, float* __restrict__ z, float* __restrict__ moments,
+                                  int N, int C, int L, int H, int W) {
+  const Geom g = make_geom(N, H, W);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.y;
+  if (p >= H * W) return;
+  const uint4 u = *reinterpret_cast<const uint4*>(enc + (long long)n * (C >> 3) * g.PL * 8 + pf8_pix(g, p, W));
+  const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+  float h[8];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { const float2 f = unpack_bf16x2(uu[e]); h[2 * e] = f.x; h[2 * e + 1] = f.y; }
+  float m[8];
+  for (int o = 0; o < 2 * L; ++o) {
+    float a = bq[o];
+    for (int i = 0; i < 2 * L; ++i) a = fmaf(wq[o * 2 * L + i], h[i], a);
+    m[o] = a;
+    if (moments) moments[((long long)n * 2 * L + o) * H * W + p] = a;
+  }
+  for (int l = 0; l < L; ++l) {
+    const float lv = fminf(fmaxf(m[L + l], -30.f), 20.f);
+    const long long idx = ((long long)n * L + l) * H * W + p;
+    z[idx] = m[l] + expf(0.5f * lv) * (noise ? noise[idx] : 0.f);
+  }
+}
+cudaError_t launch_vae_sample(const __nv_bfloat16* enc, const float* wq, const float* bq, const float* noise, float* z,
+                              float* moments, int N, int C, int L, int H, int W, cudaStream_t s) {
+  if (2 * L > 8) return cudaErrorInvalidValue;
+  vae_sample_kernel<<<dim3((H * W + 255) / 256, N), 256, 0, s>>>(enc, wq, bq, noise, z, moments, N, C, L, H, W);
+  return cudaGetLastError();
+}
+
+// post_quant_conv: 1x1 conv L -> L on fp32 NCHW (L <= 4)
+__global__ void mix1x1_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                              float* __restrict__ y, int N, int L, int HW) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.y;
+  if (p >= HW) return;
+  for (int o = 0; o < L; ++o) {
+    float a = b[o];
+    for (int i = 0; i < L; ++i) a = fmaf(w[o * L + i], x[((long long)n * L + i) * HW + p], a);
+    y[((long long)n * L + o) * HW + p] = a;
+  }
+}
+cudaError_t launch_mix1x1(const float* x, const float* w, const float* b, float* y, int N, int L, int HW, cudaStream_t s) {
+  mix1x1_kernel<<<dim3((HW + 255) / 256, N), 256, 0, s>>>(x, w, b, y, N, L, HW);
+  return cudaGetLastError();
+}
+
+}  // namespace b200ad

@@ -1,17 +1,7 @@
 // Host side of the U-Net: parameter table (diffusers naming), weight packing, activation workspace layout and
 // the launch plan that walks UNet2DModel.forward (reference call sites: audiodiffusion/pipeline_audio_diffusion.py:163,
 // :237; architecture: scripts/train_unet.py:115-137).  No tensor math happens on the host.
-#include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <map>
-#include <string>
-#include <vector>
-
-#include "../../include/b200ad.h"
-#include "conv_tc.cuh"
-#include "kernels.cuh"
+#include "net.cuh"
 
 namespace b200ad {
 
@@ -23,130 +13,16 @@ int set_err(const char* fmt, ...) {
   va_end(ap);
   return -1;
 }
-#define CK(call)                                                                  \
-  do {                                                                            \
-    cudaError_t e__ = (call);                                                     \
-    if (e__ != cudaSuccess) return set_err("%s: %s", #call, cudaGetErrorString(e__)); \
-  } while (0)
-
-struct Param {
-  std::string name;
-  std::vector<int64_t> shape;
-};
-
-struct Act {  // PF8 activation tensor
-  __nv_bfloat16* p = nullptr;
-  int C = 0, H = 0, W = 0;
-  stat_t* stats = nullptr;
-};
-
-enum OpKind { OP_TEMB, OP_CONV_IN, OP_GN, OP_CONV, OP_UPSAMPLE, OP_PARITY, OP_ATTN, OP_CONV_OUT };
-struct Op {
-  OpKind kind;
-  ConvParams conv;
-  GnApplyParams gn;
-  // generic slots
-  const __nv_bfloat16* src = nullptr;
-  __nv_bfloat16* dst = nullptr;
-  int C = 0, H = 0, W = 0;
-  ConvOutParams co;
-  float2* ss = nullptr;  // OP_GN: output of gn_finalize
-};
-
-struct Bump {  // two-pass bump allocator: base == nullptr computes sizes only
-  uint8_t* base = nullptr;
-  size_t off = 0;
-  void* take(size_t bytes) {
-    off = (off + 255) & ~(size_t)255;
-    void* r = base ? base + off : nullptr;
-    off += bytes;
-    return r;
-  }
-};
-
-struct PackJob {  // one K-segment's packed weights
-  int w_param;      // index of the fp32 weight in the table
-  int cout, cin_total, KH, KW, cin_off, ksteps;
-  PackTaps taps;
-  size_t off;       // byte offset in the packed arena
-};
 
 }  // namespace b200ad
 
 using namespace b200ad;
 
-struct b200ad_unet {
+struct b200ad_unet : NetBase {
   b200ad_unet_config cfg;
-  std::vector<Param> params;
-  std::map<std::string, int> pidx;
-  std::vector<const float*> pptr;
-  // packed arena layout
-  std::vector<PackJob> jobs;
-  std::map<std::string, size_t> seg_off;  // "<conv name>#<seg>" -> byte offset
-  size_t packed_bytes = 0;
-  size_t off_wcat = 0, off_bcat = 0, off_misc = 0;
-  std::map<std::string, size_t> misc_off;  // fused bias vectors (floats)
-  std::map<int, size_t> ident_off;         // channels -> identity weight blocks
-  int temb_rows = 0;
-  std::map<std::string, int> temb_row_off;
-  uint8_t* packed = nullptr;
-  // workspace / plan
-  int N = 0, H = 0, W = 0;
-  uint8_t* ws = nullptr;
-  size_t ws_bytes = 0;
-  std::vector<Op> plan;
-  std::map<std::string, Act> taps;
-  stat_t* stats_arena = nullptr;
-  size_t stats_bytes = 0;
-  float* temb_act = nullptr;
-  float* temb_proj = nullptr;
-  int num_sms = 148;
-  int last_launches = 0;
 };
 
 namespace b200ad {
-
-// ------------------------------------------------------------------------------ parameter table
-static void add_param(b200ad_unet* h, const std::string& name, std::vector<int64_t> shape) {
-  h->pidx[name] = (int)h->params.size();
-  h->params.push_back({name, std::move(shape)});
-}
-static void p_conv(b200ad_unet* h, const std::string& n, int cin, int cout, int k) {
-  add_param(h, n + ".weight", {cout, cin, k, k});
-  add_param(h, n + ".bias", {cout});
-}
-static void p_lin(b200ad_unet* h, const std::string& n, int cin, int cout) {
-  add_param(h, n + ".weight", {cout, cin});
-  add_param(h, n + ".bias", {cout});
-}
-static void p_gn(b200ad_unet* h, const std::string& n, int c) {
-  add_param(h, n + ".weight", {c});
-  add_param(h, n + ".bias", {c});
-}
-static void p_resnet(b200ad_unet* h, const std::string& n, int cin, int cout, int temb) {
-  p_gn(h, n + ".norm1", cin);
-  p_conv(h, n + ".conv1", cin, cout, 3);
-  p_lin(h, n + ".time_emb_proj", temb, cout);
-  p_gn(h, n + ".norm2", cout);
-  p_conv(h, n + ".conv2", cout, cout, 3);
-  if (cin != cout) p_conv(h, n + ".conv_shortcut", cin, cout, 1);
-}
-static void p_attn(b200ad_unet* h, const std::string& n, int c) {
-  p_gn(h, n + ".group_norm", c);
-  p_lin(h, n + ".to_q", c, c);
-  p_lin(h, n + ".to_k", c, c);
-  p_lin(h, n + ".to_v", c, c);
-  p_lin(h, n + ".to_out.0", c, c);
-}
-
-static std::string S(const char* fmt, ...) {
-  char buf[256];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof(buf), fmt, ap);
-  va_end(ap);
-  return buf;
-}
 
 static void build_param_table(b200ad_unet* h) {
   const b200ad_unet_config& c = h->cfg;
@@ -186,44 +62,6 @@ static void build_param_table(b200ad_unet* h) {
   p_conv(h, "conv_out", c.block_out_channels[0], c.out_channels, 3);
 }
 
-// ------------------------------------------------------------------------------ packed-arena layout
-static PackTaps taps_3x3() {
-  PackTaps t{};
-  t.ntaps = 9;
-  for (int k = 0; k < 9; ++k) { t.kh[k] = k / 3; t.kw[k] = k % 3; }
-  return t;
-}
-static PackTaps taps_1x1() {
-  PackTaps t{};
-  t.ntaps = 1;
-  t.kh[0] = 0; t.kw[0] = 0;
-  return t;
-}
-// stride-2 3x3 conv on parity plane (a, b): the taps that read input rows of parity a and columns of parity b
-static PackTaps taps_parity(int a, int b) {
-  PackTaps t{};
-  t.ntaps = 0;
-  for (int kh = 0; kh < 3; ++kh)
-    for (int kw = 0; kw < 3; ++kw) {
-      const int pa = (kh == 1) ? 0 : 1, pb = (kw == 1) ? 0 : 1;
-      if (pa == a && pb == b) { t.kh[t.ntaps] = kh; t.kw[t.ntaps] = kw; ++t.ntaps; }
-    }
-  return t;
-}
-
-static void add_job(b200ad_unet* h, Bump& b, const std::string& key, const std::string& wname, int cout, int cin_total,
-                    int K, int cin_off, int cin_cnt, const PackTaps& taps) {
-  PackJob j;
-  j.w_param = h->pidx.at(wname);
-  j.cout = cout; j.cin_total = cin_total; j.KH = K; j.KW = K; j.cin_off = cin_off; j.ksteps = cin_cnt / 16;
-  j.taps = taps;
-  const size_t bytes = (size_t)(cout / 128) * j.ksteps * taps.ntaps * CONV_B_TAP;
-  b.take(0);
-  j.off = (b.off + 255) & ~(size_t)255;
-  b.take(bytes);
-  h->seg_off[key] = j.off;
-  h->jobs.push_back(j);
-}
 
 static void build_packed_layout(b200ad_unet* h) {
   const b200ad_unet_config& c = h->cfg;
@@ -232,37 +70,11 @@ static void build_packed_layout(b200ad_unet* h) {
   b.base = nullptr;
   h->jobs.clear();
   h->temb_rows = 0;
-  // NOTE: Bump with base == nullptr returns nullptr from take(); offsets are tracked via b.off.
-  auto take_off = [&](size_t bytes) { b.take(0); size_t o = (b.off + 255) & ~(size_t)255; b.take(bytes); return o; };
   int out_c = c.block_out_channels[0];
   std::vector<int> skip_c{out_c};
   h->ident_off.clear();
-  auto need_ident = [&](int ch) {  // identity weight blocks for residual-as-K-segment
-    if (!h->ident_off.count(ch)) h->ident_off[ch] = take_off((size_t)(ch / 128) * (ch / 16) * CONV_B_TAP);
-  };
-  auto resnet = [&](const std::string& n, int ca, int cb, int co) {
-    const int cin = ca + cb;
-    // conv1 over cat(a, b): one K-segment per source (each with its own fused GroupNorm scale/shift slice)
-    add_job(h, b, n + ".conv1#0", n + ".conv1.weight", co, cin, 3, 0, ca, taps_3x3());
-    if (cb) add_job(h, b, n + ".conv1#1", n + ".conv1.weight", co, cin, 3, ca, cb, taps_3x3());
-    add_job(h, b, n + ".conv2#0", n + ".conv2.weight", co, co, 3, 0, co, taps_3x3());
-    if (cin == co) need_ident(co);
-    if (cin != co) {
-      add_job(h, b, n + ".conv2#1", n + ".conv_shortcut.weight", co, cin, 1, 0, ca, taps_1x1());
-      if (cb) add_job(h, b, n + ".conv2#2", n + ".conv_shortcut.weight", co, cin, 1, ca, cb, taps_1x1());
-      h->misc_off[n + ".bias2"] = take_off((size_t)co * 4);
-    }
-    h->temb_row_off[n] = h->temb_rows;
-    h->temb_rows += co;
-  };
-  auto attn = [&](const std::string& n, int ch) {
-    add_job(h, b, n + ".qkv#q", n + ".to_q.weight", ch, ch, 1, 0, ch, taps_1x1());
-    add_job(h, b, n + ".qkv#k", n + ".to_k.weight", ch, ch, 1, 0, ch, taps_1x1());
-    add_job(h, b, n + ".qkv#v", n + ".to_v.weight", ch, ch, 1, 0, ch, taps_1x1());
-    add_job(h, b, n + ".out#0", n + ".to_out.0.weight", ch, ch, 1, 0, ch, taps_1x1());
-    h->misc_off[n + ".bias_qkv"] = take_off((size_t)3 * ch * 4);
-    need_ident(ch);
-  };
+  auto resnet = [&](const std::string& n, int ca, int cb, int co) { layout_resnet(h, b, n, ca, cb, co, true); };
+  auto attn = [&](const std::string& n, int ch) { layout_attn(h, b, n, ch); };
   for (int i = 0; i < nb; ++i) {
     const int in_c = out_c;
     out_c = c.block_out_channels[i];
@@ -303,15 +115,9 @@ static void build_packed_layout(b200ad_unet* h) {
     }
   }
   const int D = c.block_out_channels[0] * 4;
-  h->off_wcat = take_off((size_t)h->temb_rows * D * 4);
-  h->off_bcat = take_off((size_t)h->temb_rows * 4);
+  h->off_wcat = take_off(b, (size_t)h->temb_rows * D * 4);
+  h->off_bcat = take_off(b, (size_t)h->temb_rows * 4);
   h->packed_bytes = (b.off + 255) & ~(size_t)255;
-}
-
-// ------------------------------------------------------------------------------ small device helpers
-__global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) o[i] = a[i] + (b ? b[i] : 0.f);
 }
 
 }  // namespace b200ad
@@ -329,6 +135,8 @@ extern "C" int b200ad_unet_create(const b200ad_unet_config* cfg, b200ad_unet** o
   if (cfg->out_channels > 4) return set_err("out_channels > 4 not implemented");
   b200ad_unet* h = new b200ad_unet();
   h->cfg = *cfg;
+  h->norm_groups = cfg->norm_num_groups;
+  h->norm_eps = cfg->norm_eps;
   build_param_table(h);
   build_packed_layout(h);
   h->pptr.assign(h->params.size(), nullptr);
@@ -351,28 +159,7 @@ extern "C" int b200ad_unet_set_params(b200ad_unet* h, const float* const* params
   cudaStream_t st = (cudaStream_t)stream;
   for (size_t i = 0; i < h->params.size(); ++i) h->pptr[i] = params[i];
   h->packed = (uint8_t*)packed;
-  for (const PackJob& j : h->jobs)
-    CK(launch_pack_weights(h->pptr[j.w_param], j.cout, j.cin_total, j.KH, j.KW, j.cin_off, j.ksteps, j.taps,
-                           (__nv_bfloat16*)(h->packed + j.off), st));
-  for (const auto& kv : h->ident_off) CK(launch_pack_identity(kv.first, (__nv_bfloat16*)(h->packed + kv.second), st));
-  // fused bias vectors
-  for (const auto& kv : h->misc_off) {
-    const std::string& key = kv.first;
-    float* dst = (float*)(h->packed + kv.second);
-    if (key.size() > 6 && key.compare(key.size() - 6, 6, ".bias2") == 0) {
-      const std::string n = key.substr(0, key.size() - 6);
-      const int co = (int)h->params[h->pidx.at(n + ".conv2.bias")].shape[0];
-      add_vec_kernel<<<(co + 255) / 256, 256, 0, st>>>(h->pptr[h->pidx.at(n + ".conv2.bias")],
-                                                       h->pptr[h->pidx.at(n + ".conv_shortcut.bias")], dst, co);
-      CK(cudaGetLastError());
-    } else {  // ".bias_qkv"
-      const std::string n = key.substr(0, key.size() - 9);
-      const int c = (int)h->params[h->pidx.at(n + ".to_q.bias")].shape[0];
-      CK(cudaMemcpyAsync(dst, h->pptr[h->pidx.at(n + ".to_q.bias")], c * 4, cudaMemcpyDeviceToDevice, st));
-      CK(cudaMemcpyAsync(dst + c, h->pptr[h->pidx.at(n + ".to_k.bias")], c * 4, cudaMemcpyDeviceToDevice, st));
-      CK(cudaMemcpyAsync(dst + 2 * c, h->pptr[h->pidx.at(n + ".to_v.bias")], c * 4, cudaMemcpyDeviceToDevice, st));
-    }
-  }
+  if (pack_common(h, st)) return -1;
   // concatenated time_emb_proj weights / biases
   const int D = h->cfg.block_out_channels[0] * 4;
   for (const auto& kv : h->temb_row_off) {
@@ -388,197 +175,6 @@ extern "C" int b200ad_unet_set_params(b200ad_unet* h, const float* const* params
 
 // ================================================================================= plan builder
 namespace b200ad {
-
-struct Builder {
-  b200ad_unet* h;
-  Bump ws;
-  Bump st;  // stats arena (floats, offsets in bytes)
-  std::vector<Op>* plan;
-  std::map<std::string, Act> pool;  // reusable transient buffers keyed by tag
-  int N;
-  bool nopool = false;  // B200AD_DEBUG_NOPOOL=1: every activation gets its own buffer (per-layer parity taps)
-
-  Act alloc(int C, int H, int W, bool stats) {
-    Act a;
-    a.C = C; a.H = H; a.W = W;
-    const Geom g = make_geom(N, H, W);
-    a.p = (__nv_bfloat16*)ws.take((size_t)N * (C / 8) * g.PL * 16);
-    if (stats) a.stats = (stat_t*)st.take((size_t)N * (C / 4) * 2 * sizeof(stat_t));
-    return a;
-  }
-  Act pooled(const std::string& tag, int C, int H, int W, bool stats) {
-    const std::string key = S("%s:%d:%d:%d", tag.c_str(), C, H, W);
-    if (nopool) return alloc(C, H, W, stats);
-    auto it = pool.find(key);
-    if (it == pool.end()) it = pool.emplace(key, alloc(C, H, W, false)).first;
-    Act a = it->second;
-    if (stats) a.stats = (stat_t*)st.take((size_t)N * (C / 4) * 2 * sizeof(stat_t));
-    return a;
-  }
-  const float* P(const std::string& name) const { return h->pptr[h->pidx.at(name)]; }
-  const __nv_bfloat16* WP(const std::string& key) const {
-    return h->packed ? (const __nv_bfloat16*)(h->packed + h->seg_off.at(key)) : nullptr;
-  }
-  const float* MISC(const std::string& key) const { return h->packed ? (const float*)(h->packed + h->misc_off.at(key)) : nullptr; }
-
-  void conv_common(ConvParams& p, const Act& out) {
-    const Geom g = make_geom(N, out.H, out.W);
-    p.N = N; p.H = out.H; p.W = out.W; p.Wp = g.Wp; p.lead = g.lead; p.PL = g.PL;
-    p.cout = out.C;  // work decomposition (tiles per item, item count) is filled in by launch_conv_tc
-    p.out = out.p;
-    p.stats = out.stats;
-  }
-  static void seg_taps(ConvSeg& s, const PackTaps& t, bool parity, int a, int b) {
-    s.ntaps = t.ntaps;
-    s.ht = s.hb = s.hl = s.hr = 0;
-    for (int k = 0; k < t.ntaps; ++k) {
-      if (parity) {
-        s.dh[k] = (t.kh[k] == 0) ? -1 : 0;
-        s.dw[k] = (t.kw[k] == 0) ? -1 : 0;
-      } else if (t.ntaps == 9) {
-        s.dh[k] = (signed char)(t.kh[k] - 1);
-        s.dw[k] = (signed char)(t.kw[k] - 1);
-      } else {
-        s.dh[k] = 0; s.dw[k] = 0;
-      }
-      if (s.dh[k] < 0) s.ht = 1;
-      if (s.dh[k] > 0) s.hb = 1;
-      if (s.dw[k] < 0) s.hl = 1;
-      if (s.dw[k] > 0) s.hr = 1;
-    }
-    (void)a; (void)b;
-  }
-  void set_seg(ConvSeg& s, const __nv_bfloat16* src, int C, int H, int W, const __nv_bfloat16* wpack, const PackTaps& t,
-               bool parity = false) {
-    const Geom g = make_geom(N, H, W);
-    s.src = src;
-    s.wpack = wpack;
-    s.img_stride = (long long)(C / 8) * g.PL * 8;
-    s.ksteps = C / 16;
-    s.ss = nullptr; s.ss_stride = 0; s.silu = 0;
-    seg_taps(s, t, parity, 0, 0);
-  }
-
-  // GroupNorm over cat(a, b): statistics -> per-(sample, channel) scale/shift; the apply itself is fused into the consumer
-  // conv's transform warps. Returns the [N][Ca + Cb] scale/shift array.
-  float2* gn_finalize(const Act& a, const Act* b, const std::string& norm) {
-    const int Ct = a.C + (b ? b->C : 0);
-    float2* ss = (float2*)ws.take((size_t)N * Ct * sizeof(float2));
-    Op op{};
-    op.kind = OP_GN;
-    GnApplyParams& p = op.gn;
-    p.src[0] = a.p; p.stats[0] = a.stats; p.C[0] = a.C;
-    p.src[1] = b ? b->p : nullptr; p.stats[1] = b ? b->stats : nullptr; p.C[1] = b ? b->C : 0;
-    p.gamma = P(norm + ".weight"); p.beta = P(norm + ".bias");
-    p.dst = nullptr;
-    p.N = N; p.H = a.H; p.W = a.W; p.groups = h->cfg.norm_num_groups; p.eps = h->cfg.norm_eps; p.silu = 0;
-    op.ss = ss;
-    plan->push_back(op);
-    return ss;
-  }
-  static void seg_norm(ConvSeg& s, const float2* ss, int stride, bool silu) {
-    s.ss = ss; s.ss_stride = stride; s.silu = silu ? 1 : 0;
-  }
-  const __nv_bfloat16* IDENT(int ch) const {
-    return h->packed ? (const __nv_bfloat16*)(h->packed + h->ident_off.at(ch)) : nullptr;
-  }
-
-  // ResnetBlock2D on x = cat(a, b) (b optional) -> out (raw + stats)
-  Act resnet(const std::string& n, const Act& a, const Act* b, int cout, bool out_pooled, const std::string& out_tag) {
-    const int cin = a.C + (b ? b->C : 0);
-    const int H = a.H, W = a.W;
-    const float2* ss1 = gn_finalize(a, b, n + ".norm1");
-    Act h1 = pooled("h1", cout, H, W, true);
-    {
-      Op op{};
-      op.kind = OP_CONV;
-      ConvParams& p = op.conv;
-      conv_common(p, h1);
-      p.nseg = 1;
-      set_seg(p.seg[0], a.p, a.C, H, W, WP(n + ".conv1#0"), taps_3x3());
-      seg_norm(p.seg[0], ss1, cin, true);
-      if (b) {
-        set_seg(p.seg[1], b->p, b->C, H, W, WP(n + ".conv1#1"), taps_3x3());
-        seg_norm(p.seg[1], ss1 + a.C, cin, true);
-        p.nseg = 2;
-      }
-      p.bias = P(n + ".conv1.bias");
-      p.temb = h->temb_proj + h->temb_row_off.at(n);
-      p.temb_stride = h->temb_rows;
-      plan->push_back(op);
-    }
-    const float2* ss2 = gn_finalize(h1, nullptr, n + ".norm2");
-    Act out = out_pooled ? pooled(out_tag, cout, H, W, true) : alloc(cout, H, W, true);
-    {
-      Op op{};
-      op.kind = OP_CONV;
-      ConvParams& p = op.conv;
-      conv_common(p, out);
-      p.nseg = 1;
-      set_seg(p.seg[0], h1.p, cout, H, W, WP(n + ".conv2#0"), taps_3x3());
-      seg_norm(p.seg[0], ss2, cout, true);
-      p.temb = nullptr;
-      p.temb_stride = 0;
-      if (cin != cout) {  // 1x1 conv_shortcut over the raw input(s): extra K-segments into the same accumulators
-        set_seg(p.seg[1], a.p, a.C, H, W, WP(n + ".conv2#1"), taps_1x1());
-        p.nseg = 2;
-        if (b) {
-          set_seg(p.seg[2], b->p, b->C, H, W, WP(n + ".conv2#2"), taps_1x1());
-          p.nseg = 3;
-        }
-        p.bias = MISC(n + ".bias2");
-      } else {            // identity shortcut: residual add as a 1-tap identity-weight segment over the raw input
-        set_seg(p.seg[1], a.p, a.C, H, W, IDENT(cout), taps_1x1());
-        p.nseg = 2;
-        p.bias = P(n + ".conv2.bias");
-      }
-      plan->push_back(op);
-    }
-    h->taps[n + ".h1"] = h1;
-    h->taps[n] = out;
-    return out;
-  }
-
-  Act attention(const std::string& n, const Act& x, bool out_pooled, const std::string& out_tag) {
-    const int C = x.C, H = x.H, W = x.W;
-    const float2* ssx = gn_finalize(x, nullptr, n + ".group_norm");
-    Act qkv = pooled("qkv", 3 * C, H, W, false);
-    {
-      Op op{};
-      op.kind = OP_CONV;
-      ConvParams& p = op.conv;
-      conv_common(p, qkv);
-      p.nseg = 1;
-      set_seg(p.seg[0], x.p, C, H, W, WP(n + ".qkv#q"), taps_1x1());  // q|k|v blocks are contiguous
-      seg_norm(p.seg[0], ssx, C, false);                               // GroupNorm without SiLU
-      p.bias = MISC(n + ".bias_qkv");
-      p.temb = nullptr; p.temb_stride = 0; p.stats = nullptr;
-      plan->push_back(op);
-    }
-    Act ao = pooled("attn_o", C, H, W, false);
-    {
-      Op op{};
-      op.kind = OP_ATTN;
-      op.src = qkv.p; op.dst = ao.p; op.C = C; op.H = H; op.W = W;
-      plan->push_back(op);
-    }
-    Act out = out_pooled ? pooled(out_tag, C, H, W, true) : alloc(C, H, W, true);
-    {
-      Op op{};
-      op.kind = OP_CONV;
-      ConvParams& p = op.conv;
-      conv_common(p, out);
-      p.nseg = 2;
-      set_seg(p.seg[0], ao.p, C, H, W, WP(n + ".out#0"), taps_1x1());
-      set_seg(p.seg[1], x.p, C, H, W, IDENT(C), taps_1x1());          // + residual
-      p.bias = P(n + ".to_out.0.bias");
-      p.temb = nullptr; p.temb_stride = 0;
-      plan->push_back(op);
-    }
-    h->taps[n] = out;
-    return out;
-  }
-};
 
 static int build_plan(b200ad_unet* h, uint8_t* ws_base, int N, int H, int W, size_t* ws_bytes_out) {
   const b200ad_unet_config& c = h->cfg;

@@ -83,7 +83,7 @@ int b200ad_unet_forward_step(b200ad_unet* h, const float* x, const float* t, con
 int b200ad_unet_debug_tensor(b200ad_unet* h, const char* name, float* dst, int* dims, void* stream);
 
 /* Profiling: run one fused step with a CUDA-event pair around every launch of the plan; fills per-op device time
- * (ms), op kind (0 temb, 1 conv_in, 2 gn_apply, 3 conv_tc, 4 upsample, 5 parity, 6 attention, 7 conv_out) and, for
+ * (ms), op kind (0 temb, 1 conv_in, 2 gn_finalize, 3 conv_tc, 4 unused, 5 parity_split, 6 attention, 7 conv_out) and, for
  * conv_tc launches, the algorithmic FLOPs (2*N*H*W*cout*K). Synchronises the stream. Returns the number of ops. */
 int b200ad_unet_profile_step(b200ad_unet* h, const float* x, const float* t, const float* z,
                              const b200ad_step_coef* coef, float* x_out, float* op_ms, int* op_kind,
@@ -91,6 +91,40 @@ int b200ad_unet_profile_step(b200ad_unet* h, const float* x, const float* t, con
 
 /* Number of kernel launches the last forward enqueued. */
 int b200ad_unet_last_launch_count(const b200ad_unet* h);
+
+/* ---- Latent autoencoder: replaces diffusers.AutoencoderKL as the pipeline drives it ---------------------
+ * (audiodiffusion/pipeline_audio_diffusion.py:143-147 encode + sample, :187-190 decode; architecture
+ * config/ldm_autoencoder_kl.yaml:18-28; state-dict keys as audiodiffusion/utils.py:156-303 produces them). */
+typedef struct {
+  int in_channels, out_channels;      /* 1 / 1                                                            */
+  int latent_channels;                /* z_channels = 1 (1..4 supported)                                  */
+  int layers_per_block;               /* num_res_blocks = 2                                               */
+  int num_blocks;                     /* len(ch_mult) = 4  -> spatial factor 2^(num_blocks-1) = 8         */
+  int block_out_channels[B200AD_MAX_BLOCKS]; /* ch * ch_mult = 128, 256, 512, 512                          */
+  int norm_num_groups;                /* 32                                                               */
+  float norm_eps;                     /* 1e-6                                                             */
+} b200ad_vae_config;
+
+typedef struct b200ad_vae b200ad_vae;
+
+int b200ad_vae_create(const b200ad_vae_config* cfg, b200ad_vae** out);
+void b200ad_vae_destroy(b200ad_vae* h);
+int b200ad_vae_num_params(const b200ad_vae* h);
+const char* b200ad_vae_param_name(const b200ad_vae* h, int i);
+int b200ad_vae_param_shape(const b200ad_vae* h, int i, int64_t* dims);
+size_t b200ad_vae_packed_bytes(const b200ad_vae* h);
+size_t b200ad_vae_workspace_bytes(const b200ad_vae* h, int N, int H, int W);   /* H, W: image resolution */
+int b200ad_vae_set_params(b200ad_vae* h, const float* const* params, void* packed, size_t packed_bytes, void* stream);
+int b200ad_vae_bind_workspace(b200ad_vae* h, void* workspace, size_t bytes, int N, int H, int W, void* stream);
+
+/* z = vqvae.encode(x).latent_dist.sample(): x fp32 [N, in, H, W]; noise fp32 [N, L, H/f, W/f] (the caller draws it with
+ * its own generator, as DiagonalGaussianDistribution.sample does; NULL = posterior mean, i.e. .mode()); z fp32
+ * [N, L, H/f, W/f] (NOT multiplied by scaling_factor); moments (optional) receives quant_conv's output [N, 2L, H/f, W/f]. */
+int b200ad_vae_encode(b200ad_vae* h, const float* x, const float* noise, float* z, float* moments, void* stream);
+/* x_out = vqvae.decode(z)["sample"]: z fp32 [N, L, H/f, W/f] -> fp32 [N, out, H, W]. */
+int b200ad_vae_decode(b200ad_vae* h, const float* z, float* x_out, void* stream);
+int b200ad_vae_debug_tensor(b200ad_vae* h, const char* name, float* dst, int* dims, void* stream);
+int b200ad_vae_last_launch_count(const b200ad_vae* h);
 
 /* ---- Op-level entry points (parity tests call the kernels in isolation) ------------------------------- */
 /* conv2d (KHxKW in {1x1, 3x3}, stride 1 or 2, padding KH/2) on fp32 NCHW tensors through the tcgen05

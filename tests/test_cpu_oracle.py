@@ -231,3 +231,40 @@ def test_product_fails_loudly_without_cuda():
     with pytest.raises(_lib.B200ADError):
         with torch.no_grad():
             m(torch.zeros(1, 1, 32, 32), 0)
+
+
+def test_vae_oracle_shapes_and_param_table():
+    """AutoencoderKL oracle: SURVEY §3.4 parameter counts (34.1 M encoder side, 49.5 M decoder side), latent geometry,
+    and the library's parameter table (names, order, shapes) equal to the oracle's state-dict layout."""
+    import ctypes as C
+
+    from audio_diffusion_b200 import _lib
+    from oracle import vae_oracle as vo
+
+    cfg = vo.VAEConfig()
+    sh = vo.param_shapes(cfg)
+    cnt = lambda pre: sum(int(np.prod(s)) for k, s in sh.items() if k.startswith(pre))
+    enc = cnt("encoder.") + cnt("quant_conv")
+    dec = cnt("decoder.") + cnt("post_quant_conv")
+    assert abs(enc / 1e6 - 34.1) < 0.1 and abs(dec / 1e6 - 49.5) < 0.1
+    w = vo.init_weights(cfg, seed=0)
+    x = torch.randn(1, 1, 32, 64, generator=torch.Generator().manual_seed(0))
+    m = vo.encode_moments(w, cfg, x)
+    assert m.shape == (1, 2, 4, 8)
+    z = vo.posterior_sample(m, torch.zeros(1, 1, 4, 8))
+    assert torch.equal(z, m[:, :1])
+    assert vo.decode(w, cfg, z).shape == (1, 1, 32, 64)
+
+    L = _lib.lib()
+    c = _lib.VAEConfigC(1, 1, 1, 2, 4, (C.c_int * 8)(128, 256, 512, 512), 32, 1e-6)
+    h = C.c_void_p()
+    assert L.b200ad_vae_create(C.byref(c), C.byref(h)) == 0
+    try:
+        names = [L.b200ad_vae_param_name(h, i).decode() for i in range(L.b200ad_vae_num_params(h))]
+        assert names == list(sh.keys())
+        d = (C.c_int64 * 4)()
+        for i, nm in enumerate(names):
+            k = L.b200ad_vae_param_shape(h, i, d)
+            assert tuple(d[:k]) == tuple(sh[nm]), nm
+    finally:
+        L.b200ad_vae_destroy(h)
