@@ -1,7 +1,7 @@
 """audio_diffusion_b200 — B200-native (sm_100a) engine for the teticio/audio-diffusion hot path.
 
 Public surface mirrors the reference objects the unchanged `AudioDiffusionPipeline` drives:
-`UNet2DModel`, `DDPMScheduler`, `DDIMScheduler`, `Mel`, `AudioDiffusionPipeline`.
+`UNet2DModel`, `AutoencoderKL`, `DDPMScheduler`, `DDIMScheduler`, `Mel`, `AudioDiffusionPipeline`.
 """
 __version__ = "0.1.0"
 
@@ -13,6 +13,9 @@ def __getattr__(name):
     if name == "UNet2DModel":
         from .unet import UNet2DModel
         return UNet2DModel
+    if name == "AutoencoderKL":
+        from .vae import AutoencoderKL
+        return AutoencoderKL
     if name in ("DDPMScheduler", "DDIMScheduler"):
         from . import schedulers
         return getattr(schedulers, name)

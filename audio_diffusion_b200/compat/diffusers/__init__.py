@@ -6,6 +6,7 @@ from audio_diffusion_b200.mel import Mel
 from audio_diffusion_b200.pipeline import (AudioPipelineOutput, BaseOutput, DiffusionPipeline, ImagePipelineOutput)
 from audio_diffusion_b200.schedulers import DDIMScheduler, DDPMScheduler
 from audio_diffusion_b200.unet import UNet2DModel
+from audio_diffusion_b200.vae import AutoencoderKL
 
 from .configuration_utils import ConfigMixin, register_to_config  # noqa: F401
 
@@ -30,6 +31,3 @@ class _NotBuilt:
 class UNet2DConditionModel(_NotBuilt):  # isinstance() discriminator at pipeline_audio_diffusion.py:160
     _what = "conditional U-Net"
 
-
-class AutoencoderKL(_NotBuilt):
-    _what = "latent VAE (next round)"

@@ -25,6 +25,7 @@ from . import _lib
 from .mel import Mel
 from .schedulers import DDIMScheduler, DDPMScheduler
 from .unet import UNet2DModel
+from .vae import AutoencoderKL
 
 
 class BaseOutput(dict):
@@ -93,7 +94,7 @@ class DiffusionPipeline:
                 continue
             index[k] = ["audio_diffusion_b200", type(m).__name__]
             sub = os.path.join(path, k)
-            if isinstance(m, UNet2DModel):
+            if isinstance(m, (UNet2DModel, AutoencoderKL)):
                 os.makedirs(sub, exist_ok=True)
                 with open(os.path.join(sub, "config.json"), "w") as f:
                     json.dump({kk: vv for kk, vv in m.config.items()}, f, indent=2)
@@ -119,6 +120,8 @@ class DiffusionPipeline:
                 mods[k] = None
             elif cname in ("UNet2DModel",):
                 mods[k] = load_unet(sub)
+            elif cname == "AutoencoderKL":
+                mods[k] = load_vae(sub)
             elif cname == "DDPMScheduler":
                 mods[k] = DDPMScheduler.from_pretrained(sub)
             elif cname == "DDIMScheduler":
@@ -139,6 +142,11 @@ def load_unet(sub: str) -> UNet2DModel:
     keep = ("sample_size", "in_channels", "out_channels", "down_block_types", "up_block_types", "block_out_channels",
             "layers_per_block", "attention_head_dim", "norm_num_groups", "norm_eps")
     model = UNet2DModel(**{k: cfg[k] for k in keep if k in cfg})
+    model.load_state_dict(_load_weights(sub))
+    return model
+
+
+def _load_weights(sub: str):
     st = os.path.join(sub, "diffusion_pytorch_model.safetensors")
     if os.path.exists(st):
         from safetensors.torch import load_file
@@ -151,8 +159,12 @@ def load_unet(sub: str) -> UNet2DModel:
         for a, b in ren.items():
             k = k.replace(a, b)
         fixed[k] = v.to(torch.float32)
-    model.load_state_dict(fixed)
-    return model
+    return fixed
+
+
+def load_vae(sub: str) -> AutoencoderKL:
+    """`vqvae/` component of a latent pipeline (diffusers AutoencoderKL layout)."""
+    return AutoencoderKL.from_pretrained(sub)
 
 
 class AudioDiffusionPipeline(DiffusionPipeline):
@@ -186,8 +198,6 @@ class AudioDiffusionPipeline(DiffusionPipeline):
     ):
         if encoding is not None:
             raise NotImplementedError("conditional generation (UNet2DConditionModel) is outside the b200 hot path")
-        if self.vqvae is not None:
-            raise NotImplementedError("latent audio diffusion (AutoencoderKL) is not built yet in the b200 engine")
         steps = steps or self.get_default_steps()
         self.scheduler.set_timesteps(steps)
         step_generator = step_generator or generator
@@ -209,6 +219,10 @@ class AudioDiffusionPipeline(DiffusionPipeline):
                 (input_image.height, input_image.width))
             input_image = (input_image / 255) * 2 - 1
             input_images = torch.tensor(input_image[np.newaxis, :, :], dtype=torch.float).to(device)
+            if self.vqvae is not None:  # latent audio diffusion (:143-147)
+                input_images = self.vqvae.encode(torch.unsqueeze(input_images, 0)).latent_dist.sample(
+                    generator=generator)[0]
+                input_images = 0.18215 * input_images
             if start_step > 0:
                 images[0, 0] = self.scheduler.add_noise(input_images, noise, self.scheduler.timesteps[start_step - 1])
             pixels_per_second = (
@@ -238,6 +252,11 @@ class AudioDiffusionPipeline(DiffusionPipeline):
                     images[:, :, :, :mask_start] = mask[:, step, :, :mask_start]
                 if mask_end > 0:
                     images[:, :, :, -mask_end:] = mask[:, step, :, -mask_end:]
+
+        if self.vqvae is not None:
+            # 0.18215 was scaling factor used in training to ensure unit variance (:187-190)
+            images = 1 / 0.18215 * images
+            images = self.vqvae.decode(images)["sample"]
 
         u8 = self.images_to_u8(images)                      # (B, C, H, W) uint8 on the device
         host = u8.permute(0, 2, 3, 1).cpu().numpy()

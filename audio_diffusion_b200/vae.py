@@ -151,6 +151,51 @@ class AutoencoderKL(nn.Module):
         self._ws = None
         self._ws_key = None
 
+    # ------------------------------------------------------------------ diffusers directory layout
+    _KEEP = ("in_channels", "out_channels", "down_block_types", "up_block_types", "block_out_channels",
+             "layers_per_block", "act_fn", "latent_channels", "norm_num_groups", "sample_size", "scaling_factor")
+
+    @classmethod
+    def from_pretrained(cls, path: str, subfolder: Optional[str] = None, **kw) -> "AutoencoderKL":
+        """`AutoencoderKL.from_pretrained(dir)` (scripts/train_unet.py:99-104): config.json + diffusion_pytorch_model.*;
+        raises EnvironmentError when the directory holds no model, which the reference catches to fall back to the
+        pipeline's `vqvae` component."""
+        import json
+        import os
+        sub = os.path.join(path, subfolder) if subfolder else path
+        cfgp = os.path.join(sub, "config.json")
+        if not os.path.exists(cfgp):
+            raise EnvironmentError(f"{sub} does not contain an AutoencoderKL (config.json missing)")
+        with open(cfgp) as f:
+            cfg = json.load(f)
+        model = cls(**{k: cfg[k] for k in cls._KEEP if k in cfg})
+        st = os.path.join(sub, "diffusion_pytorch_model.safetensors")
+        if os.path.exists(st):
+            from safetensors.torch import load_file
+            sd = load_file(st)
+        else:
+            sd = torch.load(os.path.join(sub, "diffusion_pytorch_model.bin"), map_location="cpu")
+        ren = {".query.": ".to_q.", ".key.": ".to_k.", ".value.": ".to_v.", ".proj_attn.": ".to_out.0."}
+        fixed = {}
+        for k, v in sd.items():
+            for a, b in ren.items():
+                k = k.replace(a, b)
+            if v.dim() == 4 and k.endswith(".weight") and (".to_" in k) and v.shape[2:] == (1, 1):
+                v = v[:, :, 0, 0]  # ldm-converted attention projections are 1x1 convs (utils.py:285-303)
+            fixed[k] = v.to(torch.float32)
+        model.load_state_dict(fixed)
+        return model
+
+    def save_pretrained(self, path: str) -> None:
+        import json
+        import os
+        os.makedirs(path, exist_ok=True)
+        with open(os.path.join(path, "config.json"), "w") as f:
+            json.dump({k: v for k, v in self.config.items()}, f, indent=2)
+        from safetensors.torch import save_file
+        save_file({k: v.detach().cpu().contiguous() for k, v in self.state_dict().items()},
+                  os.path.join(path, "diffusion_pytorch_model.safetensors"))
+
     def __del__(self):
         try:
             if getattr(self, "_h", None):

@@ -268,3 +268,31 @@ def test_vae_oracle_shapes_and_param_table():
             assert tuple(d[:k]) == tuple(sh[nm]), nm
     finally:
         L.b200ad_vae_destroy(h)
+
+
+def test_vae_bf16_rounding_floor():
+    """Derivation of the decoder tolerance in tests/test_gpu_vae.py: the fp32 oracle with every conv / linear operand and
+    output rounded to bf16 (what any bf16-storage engine does) against itself in fp32.  The encoder stays below 1.5% rms;
+    the skip-free decoder chain compounds to a few percent."""
+    import torch.nn.functional as F
+
+    from oracle import vae_oracle as vo
+
+    cfg = vo.VAEConfig()
+    w = vo.init_weights(cfg, seed=0)
+    x = torch.randn(2, 1, 64, 64, generator=torch.Generator().manual_seed(5)).clamp(-1, 1)
+    m = vo.encode_moments(w, cfg, x)
+    z = m[:, :1].contiguous()
+    y = vo.decode(w, cfg, z)
+    oc, ol = F.conv2d, F.linear
+    bf = lambda t: t.to(torch.bfloat16).to(torch.float32)
+    vo.F.conv2d = lambda a, ww, b=None, **k: bf(oc(bf(a), bf(ww), b, **k))
+    vo.F.linear = lambda a, ww, b=None: bf(ol(bf(a), bf(ww), b))
+    try:
+        m2 = vo.encode_moments(w, cfg, x)
+        y2 = vo.decode(w, cfg, z)
+    finally:
+        vo.F.conv2d, vo.F.linear = oc, ol
+    rel = lambda a, b: ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt()).item()
+    assert rel(m2, m) < 1.5e-2
+    assert 1e-2 < rel(y2, y) < 5e-2

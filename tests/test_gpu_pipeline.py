@@ -150,3 +150,69 @@ def test_shard_invariance_single_gpu(cuda):
         b = model.forward_step(x[2:].contiguous(), t, sch.step_coef(t)).clone()
     both = torch.cat([a, b])
     assert (full - both).abs().max() <= 2e-3 * full.abs().max()
+
+
+def _latent_pipe(cuda, sch):
+    """Latent audio diffusion (config C4 shape scaled down): 64x64 mel image <-> 8x8 latent, small U-Net on latents."""
+    from audio_diffusion_b200.mel import Mel
+    from audio_diffusion_b200.pipeline import AudioDiffusionPipeline
+    from audio_diffusion_b200.unet import UNet2DModel
+    from audio_diffusion_b200.vae import AutoencoderKL
+    from oracle.unet_oracle import UNetConfig, init_weights
+    from oracle.vae_oracle import VAEConfig
+    from oracle.vae_oracle import init_weights as vae_init
+    ocfg = UNetConfig(sample_size=(8, 8), **SMALL)
+    w = init_weights(ocfg, seed=5)
+    unet = UNet2DModel(sample_size=(8, 8), **SMALL)
+    unet.load_state_dict(w)
+    vcfg = VAEConfig()
+    vw = vae_init(vcfg, seed=6)
+    vae = AutoencoderKL(in_channels=1, out_channels=1, down_block_types=("DownEncoderBlock2D",) * 4,
+                        up_block_types=("UpDecoderBlock2D",) * 4, block_out_channels=vcfg.block_out_channels,
+                        layers_per_block=2, latent_channels=1)
+    vae.load_state_dict(vw)
+    pipe = AudioDiffusionPipeline(vqvae=vae.to(cuda), unet=unet.to(cuda), mel=Mel(x_res=64, y_res=64, hop_length=256),
+                                  scheduler=sch)
+    pipe.set_progress_bar_config(disable=True)
+    return pipe, (ocfg, w), (vcfg, vw)
+
+
+def test_latent_pipeline_decodes_through_vae(cuda):
+    """pipeline_audio_diffusion.py:187-190 — with a `vqvae`, the denoised latents are rescaled by 1/0.18215 and decoded.
+    The pipeline's images must equal decode(latents / 0.18215) of the same (seeded) latent loop, and the decoded
+    image must match the oracle VAE applied to those latents (bf16 tolerance, >= 90 % of pixels within 2 levels)."""
+    from audio_diffusion_b200.schedulers import DDIMScheduler
+    from oracle.vae_oracle import decode
+    sch = DDIMScheduler()
+    pipe, _, (vcfg, vw) = _latent_pipe(cuda, sch)
+    noise = torch.randn(2, 1, 8, 8, generator=torch.Generator().manual_seed(1)).to(cuda)
+    out = pipe(batch_size=2, steps=4, noise=noise.clone(), return_audio=True)
+    imgs = np.stack([np.asarray(im) for im in out.images])
+    assert imgs.shape == (2, 64, 64) and imgs.dtype == np.uint8
+    assert out.audios.shape[0] == 2 and out.audios.shape[2] == (64 - 1) * 256
+    # replay the latent loop by hand
+    sch.set_timesteps(4)
+    x = noise.clone()
+    for t in sch.timesteps:
+        x = pipe.unet.forward_step(x, t, sch.step_coef(t, 0.0), out=x)
+    lat = (1 / 0.18215 * x)
+    dec = pipe.vqvae.decode(lat)["sample"]
+    u8 = pipe.images_to_u8(dec)[:, 0].cpu().numpy()
+    assert (np.abs(u8.astype(int) - imgs.astype(int)) <= 1).mean() > 0.999
+    ref = decode(vw, vcfg, lat.cpu())
+    ref_u8 = ((ref / 2 + 0.5).clamp(0, 1) * 255).round().to(torch.uint8)[:, 0].numpy()
+    assert (np.abs(ref_u8.astype(int) - imgs.astype(int)) <= 2).mean() >= 0.9
+
+
+def test_latent_pipeline_audio_conditioning(cuda):
+    """pipeline_audio_diffusion.py:133-158 with a vqvae: the input slice is encoded to latents (sampled posterior, scaled by
+    0.18215) before noising / masking; runs end to end and returns decoded images of the mel resolution."""
+    from audio_diffusion_b200.schedulers import DDIMScheduler
+    sch = DDIMScheduler()
+    pipe, _, _ = _latent_pipe(cuda, sch)
+    rng = np.random.default_rng(0)
+    audio = (0.1 * rng.standard_normal(64 * 256 * 2)).astype(np.float32)
+    g = torch.Generator(device=cuda).manual_seed(3)
+    out = pipe(batch_size=1, raw_audio=audio, slice=0, start_step=2, steps=4, generator=g, mask_start_secs=0.1)
+    assert np.asarray(out.images[0]).shape == (64, 64)
+    assert np.isfinite(out.audios).all()

@@ -1,7 +1,12 @@
 """GPU parity of the latent autoencoder (C ABI `b200ad_vae_encode` / `b200ad_vae_decode`) against oracle/vae_oracle.py.
 
-Tolerance (stated): bf16 activations / GEMM operands with fp32 accumulation against an fp32 oracle — per layer and for
-the outputs max|err| <= 6% of the oracle tensor's max-abs and rms error <= 1.5% of its rms (same bar as the U-Net).
+Tolerance (stated): bf16 activations / GEMM operands with fp32 accumulation against an fp32 oracle.
+ * encoder (blocks, moments, latents): max|err| <= 6% of the oracle tensor's max-abs, rms error <= 1.5% of its rms — the
+   U-Net bar;
+ * decoder: a chain of ~30 convolutions with no skip connections, so bf16 rounding compounds: the fp32 oracle with its
+   conv operands/outputs merely ROUNDED to bf16 already differs from itself by 2.1-3.4% rms at the decoder output
+   (tests/test_cpu_oracle.py::test_vae_bf16_rounding_floor measures it).  Bar: rms <= 3% per decoder block, <= 5% for the
+   decoded image, max|err| <= 10%.
 """
 import os
 
@@ -34,6 +39,10 @@ def _cmp(name, got, ref, max_tol=6e-2, rms_tol=1.5e-2):
     return mx, rms
 
 
+DEC_BLOCK = dict(max_tol=1e-1, rms_tol=3e-2)
+DEC_OUT = dict(max_tol=1e-1, rms_tol=5e-2)
+
+
 def test_vae_layers_small(cuda):
     """Every block of encoder and decoder at 64x64 (latents 8x8), buffers un-pooled so each tap survives."""
     from oracle.vae_oracle import decode, encode_moments, posterior_sample
@@ -58,11 +67,12 @@ def test_vae_layers_small(cuda):
         dtaps = {}
         y_ref = decode(w, ocfg, z_ref, dtaps)
         y = model.decode(z_ref.to(cuda))["sample"]
-        for name in dtaps:
-            report.append((name,) + _cmp(name, model.debug_tensor(name).cpu(), dtaps[name]))
-        report.append(("decode",) + _cmp("decode", y.cpu(), y_ref))
         for r in report:
             print("%-48s max-rel %.4f rms-rel %.4f" % r)
+        for name in dtaps:
+            r = (name,) + _cmp(name, model.debug_tensor(name).cpu(), dtaps[name], **DEC_BLOCK)
+            print("%-48s max-rel %.4f rms-rel %.4f" % r)
+        print("%-48s max-rel %.4f rms-rel %.4f" % (("decode",) + _cmp("decode", y.cpu(), y_ref, **DEC_OUT)))
     finally:
         os.environ.pop("B200AD_DEBUG_NOPOOL", None)
 
@@ -80,7 +90,7 @@ def test_vae_pooled_nonsquare_and_mode(cuda):
     _cmp("mode", zm.cpu(), m_ref[:, :1])
     _cmp("moments", post.parameters.cpu(), m_ref)
     y = model.decode(m_ref[:, :1].to(cuda).contiguous())["sample"]
-    _cmp("decode", y.cpu(), decode(w, ocfg, m_ref[:, :1]))
+    _cmp("decode", y.cpu(), decode(w, ocfg, m_ref[:, :1]), **DEC_OUT)
     assert y.shape == (3, 1, 32, 96)
     assert model.last_launch_count > 0
 
@@ -99,4 +109,4 @@ def test_vae_c4_resolution(cuda):
     _cmp("moments", post.parameters.cpu(), m_ref)
     z = m_ref[:, :1].contiguous()
     y = model.decode(z.to(cuda))["sample"]
-    _cmp("decode", y.cpu(), decode(w, ocfg, z))
+    _cmp("decode", y.cpu(), decode(w, ocfg, z), **DEC_OUT)
