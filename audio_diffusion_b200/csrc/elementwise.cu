@@ -244,8 +244,104 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
   }
 }
 
+// cin == 1, W % 4 == 0 (every U-Net / VAE-encoder input): the plane's 72 weights stay in registers while the CTA walks
+// CIQ_ITER x 256 groups of 4 horizontally adjacent pixels; each group reads its 3 x 6 input patch once (vector load for the
+// aligned middle) and the statistics are reduced once per CTA.  Same FMA order as conv_in_kernel (bit-identical outputs).
+constexpr int CIQ_ITER = 4;
+__global__ void __launch_bounds__(256) conv_in_c1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ b, int N, int H, int W, int cout,
+                                                         __nv_bfloat16* __restrict__ out, stat_t* __restrict__ stats) {
+  __shared__ float red[8][4];
+  const Geom g = make_geom(N, H, W);
+  const int n = blockIdx.z, pl = blockIdx.y;
+  float wr[8][9], bias[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    bias[e] = __ldg(b + pl * 8 + e);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[e][t] = __ldg(w + (pl * 8 + e) * 9 + t);
+  }
+  const float* xi = x + (long long)n * H * W;
+  __nv_bfloat16* plane = out + ((long long)n * (cout >> 3) + pl) * g.PL * 8;
+  const int wq = W >> 2, nq = H * wq;
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
+  auto load_patch = [&](int q, float (&xv)[3][6]) {
+    const int h = q / wq, w0 = (q - h * wq) << 2;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int hh = h + r - 1;
+      const bool rowok = q < nq && hh >= 0 && hh < H;
+      const float* xr = xi + (long long)hh * W + w0;
+      float4 mid = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rowok) mid = __ldg(reinterpret_cast<const float4*>(xr));
+      xv[r][0] = (rowok && w0 > 0) ? __ldg(xr - 1) : 0.f;
+      xv[r][1] = mid.x; xv[r][2] = mid.y; xv[r][3] = mid.z; xv[r][4] = mid.w;
+      xv[r][5] = (rowok && w0 + 4 < W) ? __ldg(xr + 4) : 0.f;
+    }
+  };
+  float xn[3][6];  // next group's patch, fetched while the current one is being multiplied
+  load_patch(blockIdx.x * CIQ_ITER * 256 + threadIdx.x, xn);
+#pragma unroll 1
+  for (int it = 0; it < CIQ_ITER; ++it) {
+    const int q = (blockIdx.x * CIQ_ITER + it) * 256 + threadIdx.x;
+    if (q >= nq) break;
+    const int h = q / wq, w0 = (q - h * wq) << 2;
+    float xv[3][6];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) xv[r][c] = xn[r][c];
+    if (it + 1 < CIQ_ITER) load_patch(q + 256, xn);
+    float acc[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[u][e] = bias[e];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[u][e] = fmaf(xv[t / 3][u + t % 3], wr[e][t], acc[u][e]);
+    __nv_bfloat16* dst = plane + (long long)(g.lead + h * g.Wp + w0) * 8;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float* a = acc[u];
+      uint4 o;
+      o.x = pack_bf16x2(a[0], a[1]); o.y = pack_bf16x2(a[2], a[3]);
+      o.z = pack_bf16x2(a[4], a[5]); o.w = pack_bf16x2(a[6], a[7]);
+      *reinterpret_cast<uint4*>(dst + u * 8) = o;
+      s4[0] += a[0] + a[1] + a[2] + a[3];
+      s4[1] += a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3];
+      s4[2] += a[4] + a[5] + a[6] + a[7];
+      s4[3] += a[4] * a[4] + a[5] * a[5] + a[6] * a[6] + a[7] * a[7];
+    }
+  }
+  if (stats) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int sh = 16; sh >= 1; sh >>= 1) s4[k] += __shfl_xor_sync(0xffffffffu, s4[k], sh);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[warp][0] = s4[0]; red[warp][1] = s4[1]; red[warp][2] = s4[2]; red[warp][3] = s4[3]; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      float t = 0.f;
+      for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+      stat_t* dst = stats + ((long long)n * (cout >> 2) + pl * 2 + (threadIdx.x >> 1)) * 2 + (threadIdx.x & 1);
+      atomicAdd(dst, (stat_t)t);
+    }
+  }
+}
+
 cudaError_t launch_conv_in(const float* x, const float* w, const float* b, int N, int cin, int H, int W, int cout,
                            __nv_bfloat16* out, stat_t* stats, cudaStream_t s) {
+  if (cin == 1 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int nq = H * (W >> 2);
+    dim3 grid((nq + 256 * CIQ_ITER - 1) / (256 * CIQ_ITER), cout >> 3, N);
+    conv_in_c1_kernel<<<grid, 256, 0, s>>>(x, w, b, N, H, W, cout, out, stats);
+    return cudaGetLastError();
+  }
   dim3 grid((H * W + 256 * CI_PIX - 1) / (256 * CI_PIX), cout >> 3, N);
   conv_in_kernel<<<grid, 256, 0, s>>>(x, w, b, N, cin, H, W, cout, out, stats);
   return cudaGetLastError();
@@ -260,8 +356,8 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const ConvOutParams p) {
   extern __shared__ __align__(16) uint8_t osm[];
   const int planes = p.C >> 3;
   uint4* act = reinterpret_cast<uint4*>(osm);                                   // [planes][324] 16 B vectors
-  float* wsm = reinterpret_cast<float*>(osm + (size_t)planes * CO_HALO * CO_HALO * 16);  // [cout][9][C]
-  float* scale = wsm + p.cout * 9 * p.C;
+  uint2* wfrag = reinterpret_cast<uint2*>(osm + (size_t)planes * CO_HALO * CO_HALO * 16);  // [9][C/16][32] B fragments
+  float* scale = reinterpret_cast<float*>(wfrag + 9 * (p.C >> 4) * 32);
   float* shift = scale + p.C;
   float* gmean = shift + p.C;
   float* grstd = gmean + p.groups;
@@ -282,12 +378,19 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const ConvOutParams p) {
     gmean[gi] = (float)mean;
     grstd[gi] = (float)(1.0 / sqrt(fmax(q / cnt - mean * mean, 0.) + (double)p.eps));
   }
-  // weights: fp32 [cout][C][3][3] -> smem [cout][tap][C]
-  for (int i = threadIdx.x; i < p.cout * p.C * 9; i += blockDim.x) {
-    const int co = i / (p.C * 9);
-    const int rem = i - co * p.C * 9;
-    const int c = rem / 9, t = rem - c * 9;
-    wsm[(co * 9 + t) * p.C + c] = p.w[i];
+  // weights: fp32 [cout][C][3][3] -> per (tap, 16-channel k-step) the m16n8k16 B fragment (k = channel, n = cout padded
+  // to 8): lane (g, tq) holds (ch 2tq, 2tq+1 | ch 8+2tq, 9+2tq) of output channel g, zero for g >= cout
+  const int ksteps = p.C >> 4;
+  for (int i = threadIdx.x; i < 9 * ksteps * 32; i += blockDim.x) {
+    const int ln = i & 31, ks = (i >> 5) % ksteps, t = i / (32 * ksteps);
+    const int co = ln >> 2, tq = ln & 3;
+    uint2 bf = make_uint2(0u, 0u);
+    if (co < p.cout) {
+      const float* wp = p.w + ((long long)co * p.C + ks * 16 + 2 * tq) * 9 + t;
+      bf.x = pack_bf16x2(wp[0], wp[9]);
+      bf.y = pack_bf16x2(wp[72], wp[81]);
+    }
+    wfrag[i] = bf;
   }
   __syncthreads();
   for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
@@ -336,57 +439,57 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const ConvOutParams p) {
     }
   }
   __syncthreads();
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  float acc[CO_MAXOUT];
-#pragma unroll
-  for (int co = 0; co < CO_MAXOUT; ++co) acc[co] = 0.f;
-  for (int pl = 0; pl < planes; ++pl) {
+  // implicit GEMM on the warp-level tensor cores: M = 16 pixels of one tile row, N = 8 (cout padded), K = 16 channels per
+  // (tap, k-step).  Warp w owns tile rows 2w and 2w+1; A fragments are 32-bit reads of the activated halo tile.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+  const uint32_t* act32 = reinterpret_cast<const uint32_t*>(act);
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  for (int ks = 0; ks < ksteps; ++ks) {
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int kh = t / 3, kw = t - kh * 3;
-      const uint4 a = act[pl * CO_HALO * CO_HALO + (ty + kh) * CO_HALO + tx + kw];
-      float av[8];
-      float2 f;
-      f = unpack_bf16x2(a.x); av[0] = f.x; av[1] = f.y;
-      f = unpack_bf16x2(a.y); av[2] = f.x; av[3] = f.y;
-      f = unpack_bf16x2(a.z); av[4] = f.x; av[5] = f.y;
-      f = unpack_bf16x2(a.w); av[6] = f.x; av[7] = f.y;
+      const uint2 bf = wfrag[(t * ksteps + ks) * 32 + lane];
 #pragma unroll
-      for (int co = 0; co < CO_MAXOUT; ++co) {
-        if (co < p.cout) {
-          const float4* wp = reinterpret_cast<const float4*>(wsm + (co * 9 + t) * p.C + pl * 8);
-          const float4 w0v = wp[0], w1v = wp[1];
-          acc[co] += av[0] * w0v.x + av[1] * w0v.y + av[2] * w0v.z + av[3] * w0v.w +
-                     av[4] * w1v.x + av[5] * w1v.y + av[6] * w1v.z + av[7] * w1v.w;
-        }
+      for (int r = 0; r < 2; ++r) {
+        const int v0 = (2 * ks) * CO_HALO * CO_HALO + (2 * warp + r + kh) * CO_HALO + gq + kw;  // 16-byte vector index
+        const uint32_t a0 = act32[v0 * 4 + tq], a1 = act32[(v0 + 8) * 4 + tq];
+        const uint32_t a2 = act32[(v0 + CO_HALO * CO_HALO) * 4 + tq], a3 = act32[(v0 + CO_HALO * CO_HALO + 8) * 4 + tq];
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(acc[r][0]), "+f"(acc[r][1]), "+f"(acc[r][2]), "+f"(acc[r][3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf.x), "r"(bf.y));
       }
     }
   }
-  const int h = h0 + ty, w = w0 + tx;
-  if (h < p.H && w < p.W) {
+  // accumulator (r, 2j + cc) = pixel (row 2w + r, column gq + 8j), output channel 2tq + cc
 #pragma unroll
-    for (int co = 0; co < CO_MAXOUT; ++co) {
-      if (co < p.cout) {
-        const float e = acc[co] + p.b[co];
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int h = h0 + 2 * warp + r, w = w0 + gq + 8 * j;
+      if (h >= p.H || w >= p.W) continue;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int co = 2 * tq + cc;
+        if (co >= p.cout) continue;
+        const float e = acc[r][2 * j + cc] + p.b[co];
         const long long idx = (((long long)n * p.cout + co) * p.H + h) * p.W + w;
         if (p.eps_out) p.eps_out[idx] = e;
         if (p.x_out) {
           const float xv = p.x[idx];
           float x0 = (xv - p.coef.sqrt_1m_at * e) * p.coef.inv_sqrt_at;
           if (p.coef.do_clip) x0 = fminf(fmaxf(x0, -p.coef.clip), p.coef.clip);
-          float r = p.coef.c_x0 * x0 + p.coef.c_xt * xv + p.coef.c_eps * e;
-          if (p.z) r += p.coef.c_z * p.z[idx];
-          p.x_out[idx] = r;
+          float rr = p.coef.c_x0 * x0 + p.coef.c_xt * xv + p.coef.c_eps * e;
+          if (p.z) rr += p.coef.c_z * p.z[idx];
+          p.x_out[idx] = rr;
         }
       }
     }
-  }
 }
 
 cudaError_t launch_conv_out(const ConvOutParams& p, cudaStream_t s) {
-  if (p.cout > CO_MAXOUT) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)(p.C >> 3) * CO_HALO * CO_HALO * 16 +
-                      ((size_t)p.cout * 9 * p.C + 2 * p.C + 2 * p.groups) * sizeof(float);
+  if (p.cout > CO_MAXOUT || (p.C & 15)) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(p.C >> 3) * CO_HALO * CO_HALO * 16 + (size_t)9 * (p.C >> 4) * 32 * sizeof(uint2) +
+                      ((size_t)2 * p.C + 2 * p.groups) * sizeof(float);
   static size_t smem_set = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

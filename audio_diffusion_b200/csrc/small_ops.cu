@@ -2,6 +2,8 @@
 // Reference semantics: diffusers get_timestep_embedding(flip_sin_to_cos=True, freq_shift=0), TimestepEmbedding,
 // ResnetBlock2D.time_emb_proj(silu(emb)) and Attention/AttnProcessor2_0 (oracle/unet_oracle.py restates them;
 // reached from audiodiffusion/pipeline_audio_diffusion.py:163).
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace b200ad {
@@ -139,8 +141,94 @@ __global__ void __launch_bounds__(256) attention_kernel(const __nv_bfloat16* __r
   }
 }
 
+// ---- tensor-core variant (seq % 16 == 0): warp-level mma.sync, one warp per 16 queries -----------------------------
+// head_dim 8 is exactly one k-step of m16n8k8 for Q.K^T, and the P.V product is one m16n8k16 per 16 keys with n = the 8
+// output dims.  Two passes over the keys (exact row max first, then exp / sum / P.V), no online rescaling.
+__device__ __forceinline__ void mma_16x8x8_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(b0));
+}
+__device__ __forceinline__ void mma_16x8x16_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                 uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(128) attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                            __nv_bfloat16* __restrict__ out, int N, int C, int H, int W) {
+  extern __shared__ __align__(16) uint8_t amem[];
+  const int seq = H * W;
+  uint4* ks = reinterpret_cast<uint4*>(amem);  // [seq] rows of 8 bf16
+  uint4* vs = ks + seq;
+  const Geom g = make_geom(N, H, W);
+  const int head = blockIdx.x, n = blockIdx.y;
+  const int planes = C >> 3;
+  const __nv_bfloat16* base = qkv + (long long)n * 3 * planes * g.PL * 8;
+  const __nv_bfloat16* qp = base + (long long)head * g.PL * 8;
+  const __nv_bfloat16* kp = base + (long long)(planes + head) * g.PL * 8;
+  const __nv_bfloat16* vp = base + (long long)(2 * planes + head) * g.PL * 8;
+  for (int p = threadIdx.x; p < seq; p += blockDim.x) {
+    const long long pix = (long long)(g.lead + (p / W) * g.Wp + (p % W)) * 8;
+    ks[p] = *reinterpret_cast<const uint4*>(kp + pix);
+    vs[p] = *reinterpret_cast<const uint4*>(vp + pix);
+  }
+  __syncthreads();
+  const uint32_t* ks32 = reinterpret_cast<const uint32_t*>(ks);
+  const uint32_t vs_addr = (uint32_t)__cvta_generic_to_shared(vs);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
+  const float sc = 0.35355339059327373f * 1.4426950408889634f;  // 8^-0.5 * log2(e)
+  __nv_bfloat16* op = out + ((long long)n * planes + head) * g.PL * 8;
+  for (int q0 = warp * 16; q0 < seq; q0 += 64) {
+    const int qa = q0 + gq, qb = qa + 8;
+    const long long pa = (long long)(g.lead + (qa / W) * g.Wp + (qa % W)) * 8;
+    const long long pb = (long long)(g.lead + (qb / W) * g.Wp + (qb % W)) * 8;
+    const uint32_t a0 = *reinterpret_cast<const uint32_t*>(qp + pa + 2 * t);
+    const uint32_t a1 = *reinterpret_cast<const uint32_t*>(qp + pb + 2 * t);
+    float m0 = -INFINITY, m1 = -INFINITY;
+    for (int k0 = 0; k0 < seq; k0 += 8) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_16x8x8_bf16(c, a0, a1, ks32[(k0 + gq) * 4 + t]);
+      m0 = fmaxf(m0, fmaxf(c[0], c[1]));
+      m1 = fmaxf(m1, fmaxf(c[2], c[3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    m0 *= sc; m1 *= sc;
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    float l0 = 0.f, l1 = 0.f;
+    for (int k0 = 0; k0 < seq; k0 += 16) {
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_16x8x8_bf16(s0, a0, a1, ks32[(k0 + gq) * 4 + t]);
+      mma_16x8x8_bf16(s1, a0, a1, ks32[(k0 + 8 + gq) * 4 + t]);
+      const float e00 = exp2f(fmaf(s0[0], sc, -m0)), e01 = exp2f(fmaf(s0[1], sc, -m0));
+      const float e02 = exp2f(fmaf(s0[2], sc, -m1)), e03 = exp2f(fmaf(s0[3], sc, -m1));
+      const float e10 = exp2f(fmaf(s1[0], sc, -m0)), e11 = exp2f(fmaf(s1[1], sc, -m0));
+      const float e12 = exp2f(fmaf(s1[2], sc, -m1)), e13 = exp2f(fmaf(s1[3], sc, -m1));
+      l0 += (e00 + e01) + (e10 + e11);
+      l1 += (e02 + e03) + (e12 + e13);
+      uint32_t vb0, vb1;  // V[k0 .. k0+15][0..7] as the col-major B fragment: transposing ldmatrix of two 8x8 tiles
+      const uint32_t va = vs_addr + (uint32_t)(k0 + (lane & 15)) * 16u;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(vb0), "=r"(vb1) : "r"(va));
+      mma_16x8x16_bf16(o, pack_bf16x2(e00, e01), pack_bf16x2(e02, e03), pack_bf16x2(e10, e11), pack_bf16x2(e12, e13),
+                       vb0, vb1);
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    *reinterpret_cast<uint32_t*>(op + pa + 2 * t) = pack_bf16x2(o[0] * i0, o[1] * i0);
+    *reinterpret_cast<uint32_t*>(op + pb + 2 * t) = pack_bf16x2(o[2] * i1, o[3] * i1);
+  }
+}
+
 cudaError_t launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int N, int C, int H, int W, cudaStream_t s) {
   const int seq = H * W;
+  dim3 grid(C >> 3, N);
+  static const bool force_simt = [] { const char* e = getenv("B200AD_ATTN_SIMT"); return e && e[0] == '1'; }();
+  if ((seq % 16) == 0 && (size_t)seq * 32 <= 48 * 1024 && !force_simt) {
+    attention_mma_kernel<<<grid, 128, (size_t)seq * 32, s>>>(qkv, out, N, C, H, W);
+    return cudaGetLastError();
+  }
   const size_t smem = (size_t)seq * 16 * sizeof(float);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   static size_t smem_set = 48 * 1024;
@@ -149,7 +237,6 @@ cudaError_t launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int N
     if (e != cudaSuccess) return e;
     smem_set = smem;
   }
-  dim3 grid(C >> 3, N);
   const int threads = seq >= 256 ? 256 : ((seq + 31) / 32) * 32;
   attention_kernel<<<grid, threads, smem, s>>>(qkv, out, N, C, H, W);
   return cudaGetLastError();
