@@ -248,7 +248,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
 
       float ssum = 0.f, ssq = 0.f;
       const int nchunk = (p.dbg & 8) ? 0 : wi.G * (CONV_TM / 32);
-      for (int jc = half; jc < nchunk; jc += 2) {
+      const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col;
+      // one 32-pixel chunk: +bias, statistics, bf16, transpose through the warp's tile, 16-byte PF8 stores
+      auto process = [&](const uint32_t (&r)[32], int jc) {
         const int mc = wi.m0 + jc * 32;
         // validity mask of the chunk's 32 pixels (pad columns and the run-off behind the image are not stored / counted)
         uint32_t mask;
@@ -266,14 +268,20 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
             }
           }
         }
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)(jc * 32), r);
-        tmem_ld_wait();
+        if (mask == 0xffffffffu) {   // common case: no per-element predicate
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float v = __uint_as_float(r[e]) + bias;
-          if (do_stats && ((mask >> e) & 1)) { ssum += v; ssq = fmaf(v, v, ssq); }
-          *reinterpret_cast<__nv_bfloat16*>(tile + e * CONV_TROW + lane * 2) = __float2bfloat16_rn(v);
+          for (int e = 0; e < 32; ++e) {
+            const float v = __uint_as_float(r[e]) + bias;
+            ssum += v; ssq = fmaf(v, v, ssq);
+            *reinterpret_cast<__nv_bfloat16*>(tile + e * CONV_TROW + lane * 2) = __float2bfloat16_rn(v);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float v = __uint_as_float(r[e]) + bias;
+            if ((mask >> e) & 1) { ssum += v; ssq = fmaf(v, v, ssq); }
+            *reinterpret_cast<__nv_bfloat16*>(tile + e * CONV_TROW + lane * 2) = __float2bfloat16_rn(v);
+          }
         }
         __syncwarp();
         if ((mask >> lane) & 1) {
@@ -291,7 +299,23 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
           }
         }
         __syncwarp();
+      };
+      // two register sets: the TMEM load of this warp's next chunk is in flight while the current one is processed
+      uint32_t ra[32], rb[32];
+      int jc = half;
+      if (jc < nchunk) { tmem_ld32(tsrc + (uint32_t)(jc * 32), ra); tmem_ld_wait(); }
+      while (jc < nchunk) {
+        if (jc + 2 < nchunk) tmem_ld32(tsrc + (uint32_t)((jc + 2) * 32), rb);
+        process(ra, jc);
+        tmem_ld_wait();
+        jc += 2;
+        if (jc >= nchunk) break;
+        if (jc + 2 < nchunk) tmem_ld32(tsrc + (uint32_t)((jc + 2) * 32), ra);
+        process(rb, jc);
+        tmem_ld_wait();
+        jc += 2;
       }
+      if (!do_stats) { ssum = 0.f; ssq = 0.f; }
       // accumulators are drained: the MMA warp may reuse this TMEM stage
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc);

@@ -253,13 +253,23 @@ def run_b200(args):
     peak_tf, peak_hbm, how = peaks()
     value = B * world / (DDPM_STEPS * ms * 1e-3)
     e2e_val = B * world / (DDPM_STEPS * ms_e2e * 1e-3)
-    names = {0: "temb", 1: "conv_in", 2: "gn_apply", 3: "conv_tc", 4: "upsample", 5: "parity", 6: "attention", 7: "conv_out"}
+    names = {0: "temb", 1: "conv_in", 2: "gn_finalize", 3: "conv_tc", 4: "upsample", 5: "parity_split", 6: "attention", 7: "conv_out"}
     conv = prof["by_kind"].get(3, [0.0, 0.0, 0])
     step_prof_ms = sum(v[0] for v in prof["by_kind"].values())
     conv_tf = conv[1] / (conv[0] * 1e-3) / 1e12 if conv[0] > 0 else 0.0
+    # DRAM bytes per conv_tc launch come from the committed ncu launch list of this same command (profiles/); they are
+    # only valid for the default workload (batch 64, 256x256) and are null otherwise
+    traffic, traffic_src = None, None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_r01_final.json")
+    if os.path.exists(tpath) and HW == 256 and B == 64:
+        with open(tpath) as f:
+            tk = json.load(f)["kernels"].get("conv_tc_kernel")
+        if tk:
+            traffic = tk["dram_read_bytes_per_launch"] + tk["dram_write_bytes_per_launch"]
+            traffic_src = "profiles/traffic_r01_final.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over 203 launches)"
     roof = {"bound": "tensor", "kernel": "conv_tc_kernel", "achieved": conv_tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": conv_tf / peak_tf, "peak_source": f"{how} bf16 sustained (MEASURED_PEAKS.json)",
-            "traffic": None,
+            "traffic": traffic, "traffic_source": traffic_src,
             "launches_per_step": int(conv[2]), "avg_launch_ms": conv[0] / max(conv[2], 1),
             "algorithmic_gflop_per_launch": conv[1] / max(conv[2], 1) / 1e9,
             "kernel_share_of_step": conv[0] / step_prof_ms if step_prof_ms else None,
