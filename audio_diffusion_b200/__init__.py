@@ -25,4 +25,7 @@ def __getattr__(name):
     if name in ("AudioDiffusionPipeline", "DiffusionPipeline"):
         from . import pipeline
         return getattr(pipeline, name)
+    if name in ("FusedAdamW", "EMAModel", "mse_loss"):
+        from . import training
+        return getattr(training, name)
     raise AttributeError(name)

@@ -31,6 +31,11 @@ class VAEConfigC(C.Structure):
     ]
 
 
+class OptimHParamsC(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float), ("max_grad_norm", C.c_float), ("ema_decay", C.c_float), ("step", C.c_int)]
+
+
 class StepCoefC(C.Structure):
     _fields_ = [("sqrt_1m_at", C.c_float), ("inv_sqrt_at", C.c_float), ("clip", C.c_float), ("c_x0", C.c_float),
                 ("c_xt", C.c_float), ("c_eps", C.c_float), ("c_z", C.c_float), ("do_clip", C.c_int)]
@@ -74,6 +79,11 @@ SYMBOLS = {
     "b200ad_vae_decode": (_I, [_VP, _VP, _VP, _VP]),
     "b200ad_vae_debug_tensor": (_I, [_VP, C.c_char_p, _VP, C.POINTER(_I), _VP]),
     "b200ad_vae_last_launch_count": (_I, [_VP]),
+    "b200ad_optim_create": (_I, [_I, C.POINTER(C.c_int64), C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP),
+                                C.POINTER(_VP), C.POINTER(_VP)]),
+    "b200ad_optim_destroy": (None, [_VP]),
+    "b200ad_optim_step": (_I, [_VP, C.POINTER(_VP), C.POINTER(OptimHParamsC), _VP, _VP]),
+    "b200ad_mse_loss_grad": (_I, [_VP, _VP, _SZ, _VP, _VP, _VP, _VP]),
     "b200ad_conv2d_scratch_bytes": (_SZ, [_I] * 7),
     "b200ad_conv2d": (_I, [_VP] * 7 + [_I] * 7 + [_VP, _SZ, _VP]),
     "b200ad_gn_conv2d": (_I, [_VP, _VP, _VP, _I, C.c_float, _I, _VP, _VP, _VP] + [_I] * 6 + [_VP, _SZ, _VP]),

@@ -126,6 +126,31 @@ int b200ad_vae_decode(b200ad_vae* h, const float* z, float* x_out, void* stream)
 int b200ad_vae_debug_tensor(b200ad_vae* h, const char* name, float* dst, int* dims, void* stream);
 int b200ad_vae_last_launch_count(const b200ad_vae* h);
 
+/* ---- Training step, optimizer side: replaces F.mse_loss, clip_grad_norm_(1.0), torch.optim.AdamW.step and
+ * EMAModel.step of scripts/train_unet.py:258-266 (the U-Net backward itself is not built yet — DESIGN.md §6). -- */
+typedef struct {
+  float lr;              /* this step's learning rate (the caller's LR schedule, train_unet.py:174-179, :264) */
+  float beta1, beta2;    /* 0.95, 0.999                         train_unet.py:166-172 */
+  float eps;             /* 1e-8 */
+  float weight_decay;    /* 1e-6 (decoupled) */
+  float max_grad_norm;   /* 1.0 (train_unet.py:262); <= 0 disables clipping */
+  float ema_decay;       /* EMAModel's decay for this step (train_unet.py:185-190); < 0 disables the EMA update */
+  int step;              /* 1-based optimizer step (bias correction) */
+} b200ad_optim_hparams;
+typedef struct b200ad_optim b200ad_optim;
+/* Binds n_tensors fp32 device tensors (parameters, Adam moments, optional EMA shadows; sizes in elements). The handle owns
+ * only its small device-side pointer / chunk tables. */
+int b200ad_optim_create(int n_tensors, const int64_t* sizes, float* const* params, float* const* exp_avg,
+                        float* const* exp_avg_sq, float* const* ema, b200ad_optim** out);
+void b200ad_optim_destroy(b200ad_optim* h);
+/* One fused step over all tensors. grads: HOST array of n_tensors device pointers. grad_norm_out (optional, device float)
+ * receives the total gradient 2-norm before clipping. Two kernel launches. */
+int b200ad_optim_step(b200ad_optim* h, const float* const* grads, const b200ad_optim_hparams* hp, float* grad_norm_out,
+                      void* stream);
+/* loss_out[0] = mean((pred - target)^2) (device float); grad_out (optional) = 2 (pred - target) / n. scratch: 1 double. */
+int b200ad_mse_loss_grad(const float* pred, const float* target, size_t n, float* loss_out, float* grad_out,
+                         double* scratch, void* stream);
+
 /* ---- Op-level entry points (parity tests call the kernels in isolation) ------------------------------- */
 /* conv2d (KHxKW in {1x1, 3x3}, stride 1 or 2, padding KH/2) on fp32 NCHW tensors through the tcgen05
  * implicit-GEMM kernel; optional residual (fp32 NCHW, cout channels) and per-sample additive vector

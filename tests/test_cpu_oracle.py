@@ -296,3 +296,67 @@ def test_vae_bf16_rounding_floor():
     rel = lambda a, b: ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt()).item()
     assert rel(m2, m) < 1.5e-2
     assert 1e-2 < rel(y2, y) < 5e-2
+
+
+def test_train_oracle_adamw_matches_torch():
+    """The training oracle's optimizer / clipping restatement against torch itself (available here): AdamW(betas .95/.999,
+    wd 1e-6, eps 1e-8) over three steps and clip_grad_norm_(1.0) — scripts/train_unet.py:166-172, :261-263."""
+    from oracle.train_oracle import adamw_update, clip_grad_norm
+
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(37, 5, generator=g)
+    p_ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([p_ref], lr=3e-4, betas=(0.95, 0.999), weight_decay=1e-6, eps=1e-8)
+    p, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    for step in range(1, 4):
+        grad = torch.randn(37, 5, generator=g) * 3
+        p_ref.grad = grad.clone()
+        total_ref = torch.nn.utils.clip_grad_norm_([p_ref], 1.0)
+        clipped, total = clip_grad_norm({"p": grad}, 1.0)
+        assert torch.allclose(total, total_ref, rtol=1e-6)
+        assert torch.allclose(clipped["p"], p_ref.grad, rtol=1e-6, atol=1e-8)
+        opt.step()
+        adamw_update(p, clipped["p"], m, v, step, 3e-4)
+        assert torch.allclose(p, p_ref.detach(), rtol=1e-6, atol=1e-7), step
+
+
+def test_train_oracle_schedules_and_step():
+    """Cosine-with-warmup multipliers, EMA decay schedule (inv_gamma 1, power 3/4, max .9999) and one full training step
+    on a small U-Net: loss is finite, the clipped gradient norm is <= 1, parameters move, EMA follows with decay 0 first."""
+    from oracle.train_oracle import TrainState, cosine_with_warmup, ema_decay, loss_and_grads, train_step
+    from oracle.unet_oracle import UNetConfig, init_weights
+
+    assert cosine_with_warmup(0, 500, 10000) == 0.0 and cosine_with_warmup(250, 500, 10000) == 0.5
+    assert cosine_with_warmup(500, 500, 10000) == 1.0 and abs(cosine_with_warmup(5250, 500, 10000) - 0.5) < 1e-12
+    assert cosine_with_warmup(10000, 500, 10000) < 1e-12
+    assert ema_decay(0) == 0.0 and ema_decay(1) == 0.0
+    assert abs(ema_decay(2) - (1 - 2 ** -0.75)) < 1e-12 and ema_decay(10 ** 9) == 0.9999
+    # the shim's LambdaLR agrees with the oracle's multiplier
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "audio_diffusion_b200", "compat"))
+    try:
+        from diffusers.optimization import get_scheduler
+    finally:
+        sys.path.pop(0)
+    q = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([q], lr=1.0)
+    sch = get_scheduler("cosine", optimizer=opt, num_warmup_steps=5, num_training_steps=50)
+    for k in range(12):
+        assert abs(sch.get_last_lr()[0] - cosine_with_warmup(k, 5, 50)) < 1e-12
+        opt.step(); sch.step()
+
+    cfg = UNetConfig(sample_size=(16, 16), in_channels=1, out_channels=1, layers_per_block=1, block_out_channels=(128, 128),
+                     down_block_types=("DownBlock2D", "AttnDownBlock2D"), up_block_types=("AttnUpBlock2D", "UpBlock2D"))
+    w = init_weights(cfg, seed=0)
+    g = torch.Generator().manual_seed(1)
+    clean = torch.rand(2, 1, 16, 16, generator=g) * 2 - 1
+    noise = torch.randn(2, 1, 16, 16, generator=g)
+    t = torch.tensor([10, 900])
+    loss, grads, pred = loss_and_grads(w, cfg, clean, noise, t)
+    assert torch.isfinite(loss) and set(grads) == set(w) and pred.shape == noise.shape
+    st = TrainState()
+    w0 = {k: v.clone() for k, v in w.items()}
+    loss2, gnorm, lr, decay = train_step(w, cfg, st, clean, noise, t, base_lr=1e-4, warmup=0, total_steps=100)
+    assert abs(loss2 - loss) < 1e-6 and lr == 1e-4 and decay == 0.0 and st.step == 1
+    assert any(not torch.equal(w[k], w0[k]) for k in w)
+    assert all(torch.equal(st.ema[k], w[k]) for k in w)          # decay 0: shadow == parameters after step 1

@@ -1,0 +1,57 @@
+"""GPU parity of the optimizer side of the training step (b200ad_optim_step, b200ad_mse_loss_grad) against
+oracle/train_oracle.py (itself pinned against torch.optim.AdamW on the CPU).  fp32 elementwise math: tolerance 2e-6
+relative (fused multiply-adds and the order of the gradient-norm reduction differ from torch's)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fused_adamw_clip_ema_matches_oracle(cuda):
+    from audio_diffusion_b200.training import EMAModel, FusedAdamW
+    from oracle.train_oracle import adamw_update, clip_grad_norm, ema_decay
+    g = torch.Generator().manual_seed(0)
+    shapes = [(128, 1, 3, 3), (128,), (517,), (256, 128, 3, 3), (70001,)]   # odd sizes straddle the 16384-element chunks
+    ref = [torch.randn(s, generator=g) for s in shapes]
+    params = [torch.nn.Parameter(r.clone().to(cuda)) for r in ref]
+    opt = FusedAdamW(params, lr=1e-4, betas=(0.95, 0.999), weight_decay=1e-6, eps=1e-8, max_grad_norm=1.0)
+    ema = EMAModel(params, inv_gamma=1.0, power=0.75, max_value=0.9999)
+    opt.attach_ema(ema)
+    m = [torch.zeros_like(r) for r in ref]
+    v = [torch.zeros_like(r) for r in ref]
+    sh = [r.clone() for r in ref]
+    for step in range(1, 5):
+        scale = 10.0 if step != 3 else 1e-3     # step 3: total norm < 1 -> no clipping
+        grads = [torch.randn(s, generator=g) * scale for s in shapes]
+        for p, gr in zip(params, grads):
+            p.grad = gr.to(cuda)
+        lr = 1e-4 * step
+        opt.param_groups[0]["lr"] = lr          # what LambdaLR does between steps
+        opt.step()
+        ema.step(params)
+        clipped, total = clip_grad_norm({str(i): gr for i, gr in enumerate(grads)}, 1.0)
+        d = ema_decay(step, 1.0, 0.75, 0.9999)
+        assert abs(ema.cur_decay_value - d) < 1e-12
+        assert abs(opt.grad_norm.item() - total.item()) <= 2e-6 * total.item()
+        for i in range(len(ref)):
+            adamw_update(ref[i], clipped[str(i)], m[i], v[i], step, lr)
+            sh[i].sub_((1.0 - d) * (sh[i] - ref[i]))
+            assert torch.allclose(params[i].detach().cpu(), ref[i], rtol=2e-6, atol=1e-7), (step, i)
+            assert torch.allclose(opt.state[params[i]]["exp_avg_sq"].cpu(), v[i], rtol=2e-6, atol=1e-12), (step, i)
+            assert torch.allclose(ema.shadow_params[i].cpu(), sh[i], rtol=2e-6, atol=1e-7), (step, i)
+    # copy_to (train_unet.py:292-301)
+    ema.copy_to(params)
+    assert torch.equal(params[0].detach(), ema.shadow_params[0])
+
+
+def test_mse_loss_grad(cuda):
+    from audio_diffusion_b200.training import mse_loss
+    g = torch.Generator().manual_seed(1)
+    pred = torch.randn(3, 1, 64, 48, generator=g)
+    tgt = torch.randn(3, 1, 64, 48, generator=g)
+    p = pred.clone().requires_grad_(True)
+    ref = torch.nn.functional.mse_loss(p, tgt)
+    ref.backward()
+    loss, grad = mse_loss(pred.to(cuda), tgt.to(cuda))
+    assert abs(loss.item() - ref.item()) <= 1e-6 * abs(ref.item())
+    assert torch.allclose(grad.cpu(), p.grad, rtol=1e-6, atol=1e-9)
