@@ -171,6 +171,46 @@ extern "C" int b200ad_conv2d(const float* x, const float* w, const float* bias, 
                      scratch, scratch_bytes, stream);
 }
 
+// Data gradient of a stride-1 conv: gx[n][i] = sum_o sum_taps W[o][i][kh][kw] * gy[n][o][y - (kh - K/2)][x - (kw - K/2)] — the
+// same implicit GEMM with the roles of the channel dimensions swapped and the taps mirrored, so it runs on conv_tc_kernel
+// with a transposed weight packing (this is how the backward pass will reuse the forward kernel).
+extern "C" int b200ad_conv2d_dgrad(const float* gy, const float* w, float* gx, int N, int cin, int cout, int H, int W, int K,
+                                   void* scratch, size_t scratch_bytes, void* stream) {
+  if (cout % 16 || cin % 128) return set_err("conv2d_dgrad: cout %% 16 and cin %% 128 must be 0");
+  if (K != 3 && K != 1) return set_err("conv2d_dgrad: K must be 1 or 3");
+  const ConvScratch L = conv_scratch_layout(N, cout, cin, H, W, K, 1);   // GEMM view: cout -> cin channels
+  if (scratch_bytes < L.total) return set_err("conv2d_dgrad: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* sb = (uint8_t*)scratch;
+  CK(cudaMemsetAsync(sb, 0, L.total, st));
+  const Geom g = make_geom(N, H, W);
+  __nv_bfloat16* gyp = (__nv_bfloat16*)(sb + L.x);
+  __nv_bfloat16* gxp = (__nv_bfloat16*)(sb + L.out);
+  __nv_bfloat16* wp = (__nv_bfloat16*)(sb + L.wpack);
+  CK(launch_nchw_to_pf8(gy, gyp, N, cout, H, W, st));
+  PackTaps t{};
+  t.ntaps = K * K;
+  t.transpose = 1;
+  for (int k = 0; k < K * K; ++k) { t.kh[k] = K - 1 - k / K; t.kw[k] = K - 1 - k % K; }   // mirrored taps
+  CK(launch_pack_weights(w, cin, cin, K, K, 0, cout / 16, t, wp, st, cin));
+  ConvParams p{};
+  p.N = N; p.H = H; p.W = W; p.Wp = g.Wp; p.lead = g.lead; p.PL = g.PL;
+  p.cout = cin;
+  p.out = gxp; p.bias = nullptr; p.temb = nullptr; p.temb_stride = 0; p.stats = nullptr;
+  ConvSeg& s = p.seg[0];
+  s.src = gyp; s.wpack = wp; s.img_stride = (long long)(cout / 8) * g.PL * 8; s.ksteps = cout / 16; s.ntaps = K * K;
+  s.ht = s.hb = s.hl = s.hr = (K == 3) ? 1 : 0;
+  for (int k = 0; k < K * K; ++k) { s.dh[k] = (signed char)(k / K - K / 2); s.dw[k] = (signed char)(k % K - K / 2); }
+  s.ss = nullptr; s.ss_stride = 0; s.silu = 0;
+  p.nseg = 1;
+  int dev = 0, sms = 148;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CK(launch_conv_tc(p, sms, st));
+  CK(launch_pf8_to_nchw(gxp, gx, N, cin, H, W, st));
+  return 0;
+}
+
 extern "C" int b200ad_gn_conv2d(const float* x, const float* gamma, const float* beta, int groups, float eps, int silu,
                                 const float* w, const float* bias, float* y, int N, int cin, int cout, int H, int W, int K,
                                 void* scratch, size_t scratch_bytes, void* stream) {

@@ -25,7 +25,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int c
   float v[8];
 #pragma unroll
   for (int kk = 0; kk < 8; ++kk) {
-    const float* wp = w + ((long long)co * cin_total + ci0 + kk) * KH * KW;
+    const float* wp = taps.transpose ? w + ((long long)(ci0 + kk) * cout_real + co) * KH * KW
+                                     : w + ((long long)co * cin_total + ci0 + kk) * KH * KW;
     float a = 0.f;
     if (co >= cout_real) {
       // rows beyond the real output channels (cout padded to the 128-channel tile) are zero

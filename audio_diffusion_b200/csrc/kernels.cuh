@@ -8,11 +8,14 @@ namespace b200ad {
 // for input channels [cin_off, cin_off + 16*ksteps) and the listed (kh, kw) taps.
 // If fold != 0 the tap list is interpreted as groups: tap t sums the source taps whose bit is set in
 // fold_mask[t] (bit kh*KW+kw) — used to fold nearest-2x upsampling into the conv weights.
+// transpose != 0 packs the weights of the data-gradient conv: GEMM output channel = the layer's INPUT channel, GEMM input
+// channel = the layer's output channel, i.e. element W[ci][co][kh][kw] of the fp32 tensor [O][I][KH][KW] with I = cout_real.
 struct PackTaps {
   int ntaps;
   int kh[9], kw[9];
   unsigned fold_mask[9];
   int fold;
+  int transpose;
 };
 cudaError_t launch_pack_weights(const float* w, int cout, int cin_total, int KH, int KW, int cin_off, int ksteps,
                                 const PackTaps& taps, __nv_bfloat16* dst, cudaStream_t s, int cout_real = -1);

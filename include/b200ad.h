@@ -164,6 +164,12 @@ int b200ad_conv2d(const float* x, const float* w, const float* bias, const float
 int b200ad_gn_conv2d(const float* x, const float* gamma, const float* beta, int groups, float eps, int silu,
                      const float* w, const float* bias, float* y, int N, int cin, int cout, int H, int W, int K,
                      void* scratch, size_t scratch_bytes, void* stream);
+/* Data gradient of the stride-1 conv above (what autograd's conv2d backward returns for the input; first piece of the
+ * U-Net backward, scripts/train_unet.py:259): gy [N, cout, H, W], w [cout, cin, K, K] -> gx [N, cin, H, W]. Runs on the
+ * same tcgen05 kernel with transposed / mirrored weight packing. cin % 128 == 0, cout % 16 == 0;
+ * scratch >= b200ad_conv2d_scratch_bytes(N, cout, cin, H, W, K, 1). */
+int b200ad_conv2d_dgrad(const float* gy, const float* w, float* gx, int N, int cin, int cout, int H, int W, int K,
+                        void* scratch, size_t scratch_bytes, void* stream);
 /* GroupNorm(groups, eps) [+ SiLU] on fp32 NCHW through the stats + apply kernels. */
 int b200ad_group_norm(const float* x, const float* gamma, const float* beta, float* y, int N, int C, int H, int W,
                       int groups, float eps, int silu, void* scratch, size_t scratch_bytes, void* stream);

@@ -171,3 +171,26 @@ def test_upsample_conv_folded(cuda, N, C, cout, H, W):
     q = ref.view(N, cout // 4, 4, 4 * H * W)
     s_ref = torch.stack([q.sum(dim=(2, 3)), (q * q).sum(dim=(2, 3))], dim=-1)
     assert (stats.cpu() - s_ref).abs().max().item() <= 3e-2 * s_ref[..., 1].abs().max().item() + 1e-3 * 4 * H * W
+
+
+@pytest.mark.parametrize("N,cin,cout,H,W,K", [(2, 128, 256, 16, 16, 3), (1, 256, 128, 8, 24, 3), (2, 128, 128, 32, 32, 1)])
+def test_conv_dgrad_matches_autograd(cuda, N, cin, cout, H, W, K):
+    """b200ad_conv2d_dgrad (forward kernel + transposed / mirrored weight packing) == torch autograd's input gradient of
+    F.conv2d(x, w, padding=K//2) for the same upstream gradient (bf16-rounded operands, fp32 reference)."""
+    from audio_diffusion_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(7)
+    w = _bf(torch.randn(cout, cin, K, K, generator=g) / (cout * K * K) ** 0.5)
+    gy = _bf(torch.randn(N, cout, H, W, generator=g))
+    x = torch.zeros(N, cin, H, W, requires_grad=True)
+    F.conv2d(x, w, padding=K // 2).backward(gy)
+    ref = x.grad
+    gyd, wd = gy.to(cuda).contiguous(), w.to(cuda).contiguous()
+    gx = torch.empty(N, cin, H, W, device=cuda)
+    nb = L.b200ad_conv2d_scratch_bytes(N, cout, cin, H, W, K, 1)
+    scratch = torch.empty(nb, dtype=torch.uint8, device=cuda)
+    _lib.check(L.b200ad_conv2d_dgrad(gyd.data_ptr(), wd.data_ptr(), gx.data_ptr(), N, cin, cout, H, W, K,
+                                     scratch.data_ptr(), nb, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    err = (gx.cpu() - ref).abs().max().item()
+    assert err <= 1.5e-2 * ref.abs().max().item(), f"dgrad err {err} vs {ref.abs().max().item()}"
