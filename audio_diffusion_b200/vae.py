@@ -186,6 +186,21 @@ class AutoencoderKL(nn.Module):
         model.load_state_dict(fixed)
         return model
 
+    _DEPRECATED = {".query.": ".to_q.", ".key.": ".to_k.", ".value.": ".to_v.", ".proj_attn.": ".to_out.0."}
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        """Accepts the deprecated attention key names (`query/key/value/proj_attn`, possibly conv-shaped) that
+        audiodiffusion/utils.py:33-60,120-129 still writes — diffusers converts them on load
+        ([3P-recall] `_convert_deprecated_attention_blocks`)."""
+        fixed = {}
+        for k, v in state_dict.items():
+            for a, b in self._DEPRECATED.items():
+                k = k.replace(a, b)
+            if ".attentions." in k and k.endswith(".weight") and v.dim() > 2:
+                v = v.reshape(v.shape[0], v.shape[1])
+            fixed[k] = v
+        return super().load_state_dict(fixed, strict=strict, **kw)
+
     def save_pretrained(self, path: str) -> None:
         import json
         import os

@@ -111,3 +111,61 @@ def test_weight_broadcast_and_noise_sharding_gloo_world2():
     (r0, p0, m0, full), (r1, p1, m1, _) = res
     assert all(torch.equal(a, b) for a, b in zip(p0, p1))            # weights identical after the broadcast
     assert torch.equal(torch.cat([m0, m1]), full)                    # shards tile the global noise stream
+
+
+def _hf_to_ldm_vae(w, num_blocks=4):
+    """Inverse of the reference's key mapping: an `ldm` AutoencoderKL state dict (CompVis naming: down.{i}.block.{j},
+    mid.block_1 / attn_1 / block_2, up.{i} counted from the LOW-resolution end, 1x1-conv attention projections)."""
+    out = {}
+    for k, v in w.items():
+        n = k
+        n = n.replace("conv_norm_out", "norm_out")
+        for i in range(num_blocks):
+            n = n.replace(f"encoder.down_blocks.{i}.resnets.", f"encoder.down.{i}.block.")
+            n = n.replace(f"encoder.down_blocks.{i}.downsamplers.0.", f"encoder.down.{i}.downsample.")
+        if n.startswith("decoder.up_blocks."):
+            i = int(n.split(".")[2])
+            n = n.replace(f"decoder.up_blocks.{i}.resnets.", f"decoder.up.{num_blocks - 1 - i}.block.")
+            n = n.replace(f"decoder.up_blocks.{i}.upsamplers.0.", f"decoder.up.{num_blocks - 1 - i}.upsample.")
+        n = n.replace("mid_block.resnets.0", "mid.block_1").replace("mid_block.resnets.1", "mid.block_2")
+        if "mid_block.attentions.0" in n:
+            n = n.replace("mid_block.attentions.0", "mid.attn_1")
+            n = (n.replace("group_norm", "norm").replace("to_q", "q").replace("to_k", "k").replace("to_v", "v")
+                  .replace("to_out.0", "proj_out"))
+            if n.endswith(".weight") and v.dim() == 2:
+                v = v[:, :, None, None]
+        n = n.replace("conv_shortcut", "nin_shortcut")
+        out[n] = v.clone()
+    return out
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not present (GPU box)")
+def test_reference_vae_converter_feeds_the_b200_autoencoder():
+    """audiodiffusion/utils.py:156-291 (`convert_ldm_vae_checkpoint`, UNCHANGED, imported through the shim) turns an
+    ldm-format checkpoint into exactly the state dict the B200 `AutoencoderKL` loads: the library's parameter table
+    (names and shapes) is pinned against the reference's own converter."""
+    code = f"""
+import sys
+sys.path[:0] = [{ROOT!r}, {os.path.join(ROOT, 'audio_diffusion_b200', 'compat')!r}, {REF!r}, {os.path.join(ROOT, 'tests')!r}]
+import torch
+from audiodiffusion.utils import convert_ldm_vae_checkpoint            # byte-identical reference file
+from diffusers import AutoencoderKL                                     # -> audio_diffusion_b200.vae.AutoencoderKL
+from oracle.vae_oracle import VAEConfig, init_weights
+from test_cpu_dropin import _hf_to_ldm_vae
+w = init_weights(VAEConfig(), seed=3)
+ldm = _hf_to_ldm_vae(w)
+assert any(k.startswith('encoder.down.0.block.0.') for k in ldm) and 'decoder.mid.attn_1.q.weight' in ldm
+assert ldm['decoder.mid.attn_1.q.weight'].dim() == 4
+conv = convert_ldm_vae_checkpoint(dict(ldm), None)
+vae = AutoencoderKL(in_channels=1, out_channels=1, down_block_types=('DownEncoderBlock2D',) * 4,
+                    up_block_types=('UpDecoderBlock2D',) * 4, block_out_channels=(128, 256, 512, 512),
+                    layers_per_block=2, latent_channels=1)
+vae.load_state_dict(conv)                                               # strict: every key must land
+sd = vae.state_dict()
+assert set(sd) == set(w)
+for k in w:
+    assert torch.equal(sd[k], w[k]), k
+print('OK', len(sd))
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK 248" in r.stdout, r.stdout + r.stderr
