@@ -23,7 +23,7 @@ from PIL import Image
 
 from . import _lib
 from .mel import Mel
-from .schedulers import DDIMScheduler, DDPMScheduler
+from .schedulers import DDIMScheduler, DDPMScheduler, randn_tensor
 from .unet import UNet2DModel
 from .vae import AutoencoderKL
 
@@ -237,7 +237,7 @@ class AudioDiffusionPipeline(DiffusionPipeline):
             if fused:
                 z = None
                 if self.scheduler.needs_noise(t, eta):
-                    z = torch.randn(images.shape, generator=step_generator, device=images.device, dtype=images.dtype)
+                    z = randn_tensor(images.shape, step_generator, images.device, images.dtype)  # as scheduler.step draws it
                 images = self.unet.forward_step(images, t, self.scheduler.step_coef(t, eta), noise=z, out=images)
             else:
                 model_output = self.unet(images, t)["sample"]

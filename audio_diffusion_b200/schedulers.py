@@ -31,6 +31,15 @@ class SchedulerOutput(dict):
         self.pred_original_sample = pred_original_sample
 
 
+def randn_tensor(shape, generator, device, dtype=torch.float32) -> torch.Tensor:
+    """diffusers.utils.torch_utils.randn_tensor as the schedulers use it ([3P-recall] 0.24): a CPU generator with a CUDA
+    target draws on the CPU and moves the result (so CPU-seeded runs reproduce across devices)."""
+    device = torch.device(device)
+    if generator is not None and generator.device.type != device.type and generator.device.type == "cpu":
+        return torch.randn(shape, generator=generator, device="cpu", dtype=dtype).to(device)
+    return torch.randn(shape, generator=generator, device=device, dtype=dtype)
+
+
 class _SchedulerBase:
     config_name = "scheduler_config.json"
     _class_name = "SchedulerBase"
@@ -96,7 +105,7 @@ class _SchedulerBase:
         return cls(**{k: v for k, v in cfg.items() if k in known})
 
     def _noise(self, like: torch.Tensor, generator):
-        return torch.randn(like.shape, generator=generator, device=like.device, dtype=like.dtype)
+        return randn_tensor(like.shape, generator, like.device, like.dtype)
 
 
 class DDPMScheduler(_SchedulerBase):

@@ -360,3 +360,55 @@ def test_train_oracle_schedules_and_step():
     assert abs(loss2 - loss) < 1e-6 and lr == 1e-4 and decay == 0.0 and st.step == 1
     assert any(not torch.equal(w[k], w0[k]) for k in w)
     assert all(torch.equal(st.ema[k], w[k]) for k in w)          # decay 0: shadow == parameters after step 1
+
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def test_golden_vae_key_map_matches_library_table():
+    """tests/golden/vae_key_map.json (written by the reference's own converter, tools/make_golden.py) == libb200ad's
+    AutoencoderKL parameter table after diffusers' deprecated-attention renames (names AND shapes)."""
+    import ctypes as C
+    import json
+
+    from audio_diffusion_b200 import _lib
+    with open(os.path.join(GOLDEN, "vae_key_map.json")) as f:
+        gold = json.load(f)["keys"]
+    ren = {".query.": ".to_q.", ".key.": ".to_k.", ".value.": ".to_v.", ".proj_attn.": ".to_out.0."}
+    want = {}
+    for k, shape in gold:
+        for a, b in ren.items():
+            k = k.replace(a, b)
+        want[k] = tuple(shape)
+    L = _lib.lib()
+    c = _lib.VAEConfigC(1, 1, 1, 2, 4, (C.c_int * 8)(128, 256, 512, 512), 32, 1e-6)
+    h = C.c_void_p()
+    assert L.b200ad_vae_create(C.byref(c), C.byref(h)) == 0
+    try:
+        got = {}
+        d = (C.c_int64 * 4)()
+        for i in range(L.b200ad_vae_num_params(h)):
+            k = L.b200ad_vae_param_shape(h, i, d)
+            got[L.b200ad_vae_param_name(h, i).decode()] = tuple(d[:k])
+    finally:
+        L.b200ad_vae_destroy(h)
+    assert got == want
+
+
+def test_golden_pipeline_images_match_oracle_loop():
+    """tests/golden/pipeline_ddpm_small.npz was produced by the reference's unchanged AudioDiffusionPipeline.__call__
+    (tools/make_golden.py); the oracle's own loop (oracle U-Net + OracleDDPM, same noise draws) gives the same bytes."""
+    from oracle.schedulers_oracle import OracleDDPM
+    from oracle.unet_oracle import UNetConfig, init_weights, unet_forward
+    z = np.load(os.path.join(GOLDEN, "pipeline_ddpm_small.npz"))
+    cfg = UNetConfig(sample_size=(32, 32), in_channels=1, out_channels=1, layers_per_block=2, block_out_channels=(128, 256),
+                     down_block_types=("DownBlock2D", "AttnDownBlock2D"), up_block_types=("AttnUpBlock2D", "UpBlock2D"))
+    w = init_weights(cfg, seed=int(z["weight_seed"]))
+    sch = OracleDDPM()
+    sch.set_timesteps(int(z["steps"]))
+    gen = torch.Generator().manual_seed(int(z["step_seed"]))
+    x = torch.from_numpy(z["noise"]).clone()
+    for t in sch.timesteps:
+        x = sch.step(unet_forward(w, cfg, x, t), t, x, generator=gen)["prev_sample"]
+    img = ((x / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1).numpy() * 255).round().astype("uint8")[:, :, :, 0]
+    assert np.array_equal(img, z["images"])

@@ -216,3 +216,27 @@ def test_latent_pipeline_audio_conditioning(cuda):
     out = pipe(batch_size=1, raw_audio=audio, slice=0, start_step=2, steps=4, generator=g, mask_start_secs=0.1)
     assert np.asarray(out.images[0]).shape == (64, 64)
     assert np.isfinite(out.audios).all()
+
+
+def test_golden_reference_driven_images(cuda):
+    """tests/golden/pipeline_ddpm_small.npz: uint8 images returned by the REFERENCE's own pipeline file (driving the fp32
+    oracle U-Net, tools/make_golden.py). The B200 pipeline on the same noise, weights and CPU step generator reproduces
+    them to the stated trajectory tolerance (>= 90 % of pixels within 2 grey levels)."""
+    import os
+    from audio_diffusion_b200.mel import Mel
+    from audio_diffusion_b200.pipeline import AudioDiffusionPipeline
+    from audio_diffusion_b200.schedulers import DDPMScheduler
+    from audio_diffusion_b200.unet import UNet2DModel
+    from oracle.unet_oracle import UNetConfig, init_weights
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pipeline_ddpm_small.npz"))
+    w = init_weights(UNetConfig(sample_size=(32, 32), **SMALL), seed=int(z["weight_seed"]))
+    m = UNet2DModel(sample_size=(32, 32), **SMALL)
+    m.load_state_dict(w)
+    pipe = AudioDiffusionPipeline(vqvae=None, unet=m.to(cuda), mel=Mel(x_res=32, y_res=32, hop_length=512, n_iter=2),
+                                  scheduler=DDPMScheduler())
+    pipe.set_progress_bar_config(disable=True)
+    imgs = pipe(batch_size=2, steps=int(z["steps"]), noise=torch.from_numpy(z["noise"]).to(cuda),
+                step_generator=torch.Generator().manual_seed(int(z["step_seed"])), return_audio=False)
+    got = np.stack([np.asarray(im) for im in imgs]).astype(int)
+    frac = (np.abs(got - z["images"].astype(int)) <= 2).mean()
+    assert frac >= 0.9, frac
