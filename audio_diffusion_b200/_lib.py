@@ -66,6 +66,13 @@ SYMBOLS = {
                                       C.POINTER(_I), C.POINTER(C.c_double), _I, _VP]),
     "b200ad_unet_debug_tensor": (_I, [_VP, C.c_char_p, _VP, C.POINTER(_I), _VP]),
     "b200ad_unet_last_launch_count": (_I, [_VP]),
+    "b200ad_unet_set_training": (_I, [_VP, _I]),
+    "b200ad_unet_grad_floats": (_SZ, [_VP]),
+    "b200ad_unet_grad_offset": (_SZ, [_VP, _I]),
+    "b200ad_unet_backward_bytes": (_SZ, [_VP]),
+    "b200ad_unet_bind_backward": (_I, [_VP, _VP, _SZ, _VP, _VP]),
+    "b200ad_unet_backward": (_I, [_VP, _VP, _VP, _VP]),
+    "b200ad_unet_backward_launch_count": (_I, [_VP]),
     "b200ad_vae_create": (_I, [C.POINTER(VAEConfigC), C.POINTER(_VP)]),
     "b200ad_vae_destroy": (None, [_VP]),
     "b200ad_vae_num_params": (_I, [_VP]),
@@ -87,6 +94,8 @@ SYMBOLS = {
     "b200ad_conv2d_scratch_bytes": (_SZ, [_I] * 7),
     "b200ad_conv2d": (_I, [_VP] * 7 + [_I] * 7 + [_VP, _SZ, _VP]),
     "b200ad_conv2d_dgrad": (_I, [_VP, _VP, _VP] + [_I] * 6 + [_VP, _SZ, _VP]),
+    "b200ad_conv2d_wgrad_scratch_bytes": (_SZ, [_I] * 5),
+    "b200ad_conv2d_wgrad": (_I, [_VP, _VP, _VP] + [_I] * 6 + [_VP, _SZ, _VP]),
     "b200ad_gn_conv2d": (_I, [_VP, _VP, _VP, _I, C.c_float, _I, _VP, _VP, _VP] + [_I] * 6 + [_VP, _SZ, _VP]),
     "b200ad_group_norm": (_I, [_VP] * 4 + [_I] * 5 + [C.c_float, _I, _VP, _SZ, _VP]),
     "b200ad_mel_scratch_bytes": (_SZ, [C.POINTER(MelConfigC), _I]),

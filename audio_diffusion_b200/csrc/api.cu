@@ -4,6 +4,7 @@
 
 #include "../../include/b200ad.h"
 #include "conv_tc.cuh"
+#include "bwd_kernels.cuh"
 #include "kernels.cuh"
 
 namespace b200ad {
@@ -209,6 +210,38 @@ extern "C" int b200ad_conv2d_dgrad(const float* gy, const float* w, float* gx, i
   CK(launch_conv_tc(p, sms, st));
   CK(launch_pf8_to_nchw(gxp, gx, N, cin, H, W, st));
   return 0;
+}
+
+// Weight gradient of the stride-1 conv: dw[o][i][kh][kw] = sum_{n,y,x} gy[n][o][y][x] * a[n][i][y + kh - K/2][x + kw - K/2].
+extern "C" int b200ad_conv2d_wgrad(const float* gy, const float* a, float* dw, int N, int cin, int cout, int H, int W, int K,
+                                   void* scratch, size_t scratch_bytes, void* stream) {
+  if (cout % 128 || cin % 32) return set_err("conv2d_wgrad: cout %% 128 and cin %% 32 must be 0");
+  if (K != 3 && K != 1) return set_err("conv2d_wgrad: K must be 1 or 3");
+  const Geom g = make_geom(N, H, W);
+  const size_t gyb = al((size_t)N * (cout / 8) * g.PL * 16), ab = al((size_t)N * (cin / 8) * g.PL * 16);
+  if (scratch_bytes < gyb + ab) return set_err("conv2d_wgrad: scratch too small (%zu < %zu)", scratch_bytes, gyb + ab);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* sb = (uint8_t*)scratch;
+  CK(cudaMemsetAsync(sb, 0, gyb + ab, st));
+  __nv_bfloat16* gyp = (__nv_bfloat16*)sb;
+  __nv_bfloat16* ap = (__nv_bfloat16*)(sb + gyb);
+  CK(launch_nchw_to_pf8(gy, gyp, N, cout, H, W, st));
+  CK(launch_nchw_to_pf8(a, ap, N, cin, H, W, st));
+  CK(cudaMemsetAsync(dw, 0, (size_t)cout * cin * K * K * sizeof(float), st));
+  int dev = 0, sms = 148;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  WgradDesc d{};
+  d.gy = gyp; d.act = ap; d.dw = dw; d.N = N; d.H = H; d.W = W; d.cout = cout; d.cin = cin;
+  d.gy_img_planes = cout / 8; d.act_img_planes = cin / 8; d.cin_total = cin; d.ci_off = 0; d.ntaps_total = K * K;
+  d.ntaps = K * K;
+  for (int t = 0; t < K * K; ++t) { d.dh[t] = t / K - K / 2; d.dw_[t] = t % K - K / 2; d.tapidx[t] = t; }
+  CK(launch_wgrad_tc(d, sms, st));
+  return 0;
+}
+extern "C" size_t b200ad_conv2d_wgrad_scratch_bytes(int N, int cin, int cout, int H, int W) {
+  const Geom g = make_geom(N, H, W);
+  return al((size_t)N * (cout / 8) * g.PL * 16) + al((size_t)N * (cin / 8) * g.PL * 16);
 }
 
 extern "C" int b200ad_gn_conv2d(const float* x, const float* gamma, const float* beta, int groups, float eps, int silu,

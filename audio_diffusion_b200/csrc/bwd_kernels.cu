@@ -1,0 +1,556 @@
+// Memory-bound pieces of the U-Net backward pass (scripts/train_unet.py:259 `accelerator.backward(loss)`): GroupNorm(+SiLU)
+// backward, per-channel gradient sums (bias / time-embedding gradients), head_dim-8 attention backward, the cin = 1 /
+// cout = 1 convolution weight gradients, the timestep-MLP linears, and small helpers. Gradients of activations are PF8
+// bf16 (what autocast gives the reference); parameter gradients are accumulated in fp32.
+// Oracle: torch autograd over oracle/unet_oracle.py (oracle/train_oracle.py::loss_and_grads).
+#include "bwd_kernels.cuh"
+
+namespace b200ad {
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int sh = 16; sh >= 1; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
+  return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { const float2 t = unpack_bf16x2(u[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// GroupNorm (+SiLU) backward over the channel concatenation of up to two raw sources.
+//   y = gamma * xhat + beta, a = silu(y) (or y);  gy = ga * silu'(y)
+//   S1[n][c] = sum_pix gy, S2[n][c] = sum_pix gy * xhat;  dbeta = sum_n S1, dgamma = sum_n S2
+//   gx = rstd * (gamma * gy - (A + xhat * B) / M),  A = sum_{c in group} gamma_c S1_c, B = sum gamma_c S2_c, M = cpg*H*W
+constexpr int GB_THREADS = 256;
+constexpr int GB_PIX = 4096;   // pixels per CTA in the reduction pass
+
+struct GnConst {   // per-channel constants of one 8-channel plane, built per thread from shared tables
+  float scale[8], shift[8];
+};
+
+__device__ __forceinline__ void group_stats(const GnBwdParams& p, int n, float* gmean, float* grstd) {
+  const int Ct = p.C[0] + p.C[1];
+  const int cpg = Ct / p.groups;
+  for (int gi = threadIdx.x; gi < p.groups; gi += blockDim.x) {
+    double s = 0., q = 0.;
+    for (int c = gi * cpg; c < (gi + 1) * cpg; c += 4) {
+      const stat_t* st = (c < p.C[0]) ? p.stats[0] + ((long long)n * (p.C[0] >> 2) + (c >> 2)) * 2
+                                     : p.stats[1] + ((long long)n * (p.C[1] >> 2) + ((c - p.C[0]) >> 2)) * 2;
+      s += st[0];
+      q += st[1];
+    }
+    const double cnt = (double)cpg * (double)p.H * (double)p.W;
+    const double mean = s / cnt;
+    gmean[gi] = (float)mean;
+    grstd[gi] = (float)(1.0 / sqrt(fmax(q / cnt - mean * mean, 0.) + (double)p.eps));
+  }
+}
+
+__device__ __forceinline__ float silu_grad(float y) {
+  const float sig = 1.0f / (1.0f + __expf(-y));
+  return sig * (1.0f + y * (1.0f - sig));
+}
+
+// pass 1: grid (pixel chunks, planes, N). Thread-local sums over the CTA's pixels of one 8-channel plane.
+__global__ void __launch_bounds__(GB_THREADS) gn_bwd_reduce_kernel(const GnBwdParams p) {
+  __shared__ float gmean[64], grstd[64];
+  __shared__ float red[GB_THREADS / 32][16];
+  const int Ct = p.C[0] + p.C[1];
+  const int n = blockIdx.z, pl = blockIdx.y;
+  const int cpg = Ct / p.groups;
+  const Geom g = make_geom(p.N, p.H, p.W);
+  group_stats(p, n, gmean, grstd);
+  __syncthreads();
+  const int planes0 = p.C[0] >> 3;
+  const __nv_bfloat16* xs = (pl < planes0) ? p.src[0] + ((long long)n * planes0 + pl) * g.PL * 8
+                                          : p.src[1] + ((long long)n * (p.C[1] >> 3) + (pl - planes0)) * g.PL * 8;
+  const __nv_bfloat16* gs = p.ga + ((long long)n * (Ct >> 3) + pl) * g.PL * 8;
+  float mean[8], rstd[8], gam[8], bet[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = pl * 8 + e, gi = c / cpg;
+    mean[e] = gmean[gi]; rstd[e] = grstd[gi]; gam[e] = p.gamma[c]; bet[e] = p.beta[c];
+  }
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int hw = p.H * p.W;
+  const int pend = min(hw, (int)(blockIdx.x + 1) * GB_PIX);
+  for (int pidx = blockIdx.x * GB_PIX + threadIdx.x; pidx < pend; pidx += GB_THREADS) {
+    const int h = pidx / p.W, w = pidx - h * p.W;
+    const long long pix = (long long)(g.lead + h * g.Wp + w) * 8;
+    float xv[8], gv[8];
+    unpack8(*reinterpret_cast<const uint4*>(xs + pix), xv);
+    unpack8(*reinterpret_cast<const uint4*>(gs + pix), gv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float xh = (xv[e] - mean[e]) * rstd[e];
+      float gy = gv[e];
+      if (p.silu) gy *= silu_grad(gam[e] * xh + bet[e]);
+      s1[e] += gy;
+      s2[e] = fmaf(gy, xh, s2[e]);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float a = warp_sum_f(s1[e]), b = warp_sum_f(s2[e]);
+    if (lane == 0) { red[warp][e] = a; red[warp][8 + e] = b; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float t = 0.f;
+    for (int k = 0; k < GB_THREADS / 32; ++k) t += red[k][threadIdx.x];
+    const int e = threadIdx.x & 7, which = threadIdx.x >> 3;
+    atomicAdd(p.sums + ((long long)n * Ct + pl * 8 + e) * 2 + which, t);
+  }
+}
+
+// dgamma / dbeta: one thread per channel sums over the samples
+__global__ void gn_bwd_param_kernel(const GnBwdParams p) {
+  const int Ct = p.C[0] + p.C[1];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Ct) return;
+  float a = 0.f, b = 0.f;
+  for (int n = 0; n < p.N; ++n) {
+    a += p.sums[((long long)n * Ct + c) * 2];
+    b += p.sums[((long long)n * Ct + c) * 2 + 1];
+  }
+  atomicAdd(p.dbeta + c, a);
+  atomicAdd(p.dgamma + c, b);
+}
+
+// pass 2: grid (pixel chunks of 256, planes, N): gx (+ optional addends) for one pixel x one plane per thread
+__global__ void __launch_bounds__(GB_THREADS) gn_bwd_apply_kernel(const GnBwdParams p) {
+  __shared__ float gmean[64], grstd[64], gA[64], gB[64];
+  const int Ct = p.C[0] + p.C[1];
+  const int n = blockIdx.z, pl = blockIdx.y;
+  const int cpg = Ct / p.groups;
+  const Geom g = make_geom(p.N, p.H, p.W);
+  group_stats(p, n, gmean, grstd);
+  const float invM = 1.0f / ((float)cpg * (float)p.H * (float)p.W);
+  for (int gi = threadIdx.x; gi < p.groups; gi += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
+      a = fmaf(p.gamma[c], p.sums[((long long)n * Ct + c) * 2], a);
+      b = fmaf(p.gamma[c], p.sums[((long long)n * Ct + c) * 2 + 1], b);
+    }
+    gA[gi] = a * invM;
+    gB[gi] = b * invM;
+  }
+  __syncthreads();
+  const int pidx = blockIdx.x * GB_THREADS + threadIdx.x;
+  if (pidx >= p.H * p.W) return;
+  const int h = pidx / p.W, w = pidx - h * p.W;
+  const long long pix = (long long)(g.lead + h * g.Wp + w) * 8;
+  const int planes0 = p.C[0] >> 3;
+  const bool first = pl < planes0;
+  const int lp = first ? pl : pl - planes0;                 // plane inside its own source / destination
+  const int lplanes = first ? planes0 : (p.C[1] >> 3);
+  const __nv_bfloat16* xs = (first ? p.src[0] : p.src[1]) + ((long long)n * lplanes + lp) * g.PL * 8;
+  float xv[8], gv[8], o[8];
+  unpack8(*reinterpret_cast<const uint4*>(xs + pix), xv);
+  unpack8(*reinterpret_cast<const uint4*>(p.ga + ((long long)n * (Ct >> 3) + pl) * g.PL * 8 + pix), gv);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = pl * 8 + e, gi = c / cpg;
+    const float rs = grstd[gi], xh = (xv[e] - gmean[gi]) * rs, gam = p.gamma[c];
+    float gy = gv[e];
+    if (p.silu) gy *= silu_grad(gam * xh + p.beta[c]);
+    o[e] = rs * (gam * gy - (gA[gi] + xh * gB[gi]));
+  }
+  if (p.addS) {
+    float av[8];
+    unpack8(*reinterpret_cast<const uint4*>(p.addS + ((long long)n * (Ct >> 3) + pl) * g.PL * 8 + pix), av);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] += av[e];
+  }
+  if (p.add0 && first) {
+    float av[8];
+    unpack8(*reinterpret_cast<const uint4*>(p.add0 + ((long long)n * planes0 + pl) * g.PL * 8 + pix), av);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] += av[e];
+  }
+  __nv_bfloat16* dp = (first ? p.dst[0] : p.dst[1]) + ((long long)n * lplanes + lp) * g.PL * 8;
+  *reinterpret_cast<uint4*>(dp + pix) = pack8(o);
+}
+
+cudaError_t launch_gn_bwd(const GnBwdParams& p, cudaStream_t s) {
+  const int Ct = p.C[0] + p.C[1];
+  if (p.groups > 64 || (Ct % p.groups)) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(p.sums, 0, (size_t)p.N * Ct * 2 * sizeof(float), s);
+  if (e != cudaSuccess) return e;
+  const int hw = p.H * p.W;
+  gn_bwd_reduce_kernel<<<dim3((hw + GB_PIX - 1) / GB_PIX, Ct >> 3, p.N), GB_THREADS, 0, s>>>(p);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (p.dgamma) {
+    gn_bwd_param_kernel<<<(Ct + 127) / 128, 128, 0, s>>>(p);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  gn_bwd_apply_kernel<<<dim3((hw + GB_THREADS - 1) / GB_THREADS, Ct >> 3, p.N), GB_THREADS, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// out[n][c] = sum over pixels of src[n][c][.] (PF8 bf16 -> fp32).  `out` must be zeroed by the caller (launcher does).
+__global__ void __launch_bounds__(GB_THREADS) chan_sum_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ out,
+                                                              int N, int C, int img_planes, int H, int W) {
+  __shared__ float red[GB_THREADS / 32][8];
+  const int n = blockIdx.z, pl = blockIdx.y;
+  const Geom g = make_geom(N, H, W);
+  const __nv_bfloat16* sp = src + ((long long)n * img_planes + pl) * g.PL * 8;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int hw = H * W;
+  const int pend = min(hw, (int)(blockIdx.x + 1) * GB_PIX);
+  for (int pidx = blockIdx.x * GB_PIX + threadIdx.x; pidx < pend; pidx += GB_THREADS) {
+    const int h = pidx / W, w = pidx - h * W;
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(sp + (long long)(g.lead + h * g.Wp + w) * 8), v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] += v[e];
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float a = warp_sum_f(s[e]);
+    if (lane == 0) red[warp][e] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = 0.f;
+    for (int k = 0; k < GB_THREADS / 32; ++k) t += red[k][threadIdx.x];
+    atomicAdd(out + (long long)n * C + pl * 8 + threadIdx.x, t);
+  }
+}
+cudaError_t launch_chan_sum(const __nv_bfloat16* src, float* out, int N, int C, int img_planes, int H, int W, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * C * sizeof(float), s);
+  if (e != cudaSuccess) return e;
+  chan_sum_kernel<<<dim3((H * W + GB_PIX - 1) / GB_PIX, C >> 3, N), GB_THREADS, 0, s>>>(src, out, N, C, img_planes, H, W);
+  return cudaGetLastError();
+}
+
+// dst[c] += sum_n src[n][c]   (bias gradients);  dst2 (optional) receives the same sum
+__global__ void reduce_n_add_kernel(const float* __restrict__ src, float* __restrict__ dst, float* __restrict__ dst2, int N,
+                                    int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f;
+  for (int n = 0; n < N; ++n) a += src[(long long)n * C + c];
+  dst[c] += a;
+  if (dst2) dst2[c] += a;
+}
+cudaError_t launch_reduce_n_add(const float* src, float* dst, float* dst2, int N, int C, cudaStream_t s) {
+  reduce_n_add_kernel<<<(C + 127) / 128, 128, 0, s>>>(src, dst, dst2, N, C);
+  return cudaGetLastError();
+}
+
+// copy rows: dst[n][doff + c] = src[n][c]  (time-embedding gradient rows of one resnet into g_proj[N][rows])
+__global__ void scatter_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int C, int dstride, int doff) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i - n * C;
+  dst[(long long)n * dstride + doff + c] = src[i];
+}
+cudaError_t launch_scatter_rows(const float* src, float* dst, int N, int C, int dstride, int doff, cudaStream_t s) {
+  scatter_rows_kernel<<<(N * C + 255) / 256, 256, 0, s>>>(src, dst, N, C, dstride, doff);
+  return cudaGetLastError();
+}
+
+// dst += src over whole PF8 buffers (pads are zero on both sides)
+__global__ void pf8_add_kernel(__nv_bfloat16* __restrict__ dst, const __nv_bfloat16* __restrict__ src, long long nvec) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  float a[8], b[8];
+  unpack8(reinterpret_cast<const uint4*>(dst)[i], a);
+  unpack8(reinterpret_cast<const uint4*>(src)[i], b);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] += b[e];
+  reinterpret_cast<uint4*>(dst)[i] = pack8(a);
+}
+cudaError_t launch_pf8_add(__nv_bfloat16* dst, const __nv_bfloat16* src, int N, int C, int H, int W, cudaStream_t s) {
+  const Geom g = make_geom(N, H, W);
+  const long long nvec = (long long)N * (C >> 3) * g.PL;
+  pf8_add_kernel<<<(unsigned)((nvec + 255) / 256), 256, 0, s>>>(dst, src, nvec);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Attention backward, heads of dim 8 (one plane each).  grid (heads, N).  qkv: PF8 3C; go: gradient of the attention output
+// (PF8 C); gqkv: PF8 3C.  Phase 1 (thread per query): row max / sum, D_i = sum_j P_ij dP_ij, dQ_i.  Phase 2 (thread per
+// key): dK_j, dV_j with P recomputed from the saved row statistics.
+__global__ void __launch_bounds__(256) attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                            const __nv_bfloat16* __restrict__ go,
+                                                            __nv_bfloat16* __restrict__ gqkv, int N, int C, int H, int W) {
+  extern __shared__ float ab[];
+  const int seq = H * W;
+  float* qs = ab;                  // [seq][8]
+  float* ks = qs + seq * 8;
+  float* vs = ks + seq * 8;
+  float* ds = vs + seq * 8;        // dO
+  float* rm = ds + seq * 8;        // row max
+  float* rl = rm + seq;            // 1 / row sum
+  float* rd = rl + seq;            // D_i
+  const Geom g = make_geom(N, H, W);
+  const int head = blockIdx.x, n = blockIdx.y, planes = C >> 3;
+  const __nv_bfloat16* base = qkv + (long long)n * 3 * planes * g.PL * 8;
+  const __nv_bfloat16* gop = go + ((long long)n * planes + head) * g.PL * 8;
+  for (int p = threadIdx.x; p < seq; p += blockDim.x) {
+    const long long pix = (long long)(g.lead + (p / W) * g.Wp + (p % W)) * 8;
+    float t[8];
+    unpack8(*reinterpret_cast<const uint4*>(base + (long long)head * g.PL * 8 + pix), t);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) qs[p * 8 + e] = t[e];
+    unpack8(*reinterpret_cast<const uint4*>(base + (long long)(planes + head) * g.PL * 8 + pix), t);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ks[p * 8 + e] = t[e];
+    unpack8(*reinterpret_cast<const uint4*>(base + (long long)(2 * planes + head) * g.PL * 8 + pix), t);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) vs[p * 8 + e] = t[e];
+    unpack8(*reinterpret_cast<const uint4*>(gop + pix), t);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ds[p * 8 + e] = t[e];
+  }
+  __syncthreads();
+  const float sc = 0.35355339059327373f;  // 8^-0.5
+  __nv_bfloat16* gbase = gqkv + (long long)n * 3 * planes * g.PL * 8;
+  for (int i = threadIdx.x; i < seq; i += blockDim.x) {
+    float q[8], dO[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { q[e] = qs[i * 8 + e] * sc; dO[e] = ds[i * 8 + e]; }
+    float mx = -INFINITY;
+    for (int j = 0; j < seq; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s = fmaf(q[e], ks[j * 8 + e], s);
+      mx = fmaxf(mx, s);
+    }
+    float l = 0.f, dsum = 0.f;
+    for (int j = 0; j < seq; ++j) {
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s = fmaf(q[e], ks[j * 8 + e], s); dp = fmaf(dO[e], vs[j * 8 + e], dp); }
+      const float ex = __expf(s - mx);
+      l += ex;
+      dsum = fmaf(ex, dp, dsum);
+    }
+    const float il = 1.0f / l, D = dsum * il;
+    float dq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < seq; ++j) {
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s = fmaf(q[e], ks[j * 8 + e], s); dp = fmaf(dO[e], vs[j * 8 + e], dp); }
+      const float dS = __expf(s - mx) * il * (dp - D);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dq[e] = fmaf(dS, ks[j * 8 + e], dq[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dq[e] *= sc;
+    rm[i] = mx; rl[i] = il; rd[i] = D;
+    const long long pix = (long long)(g.lead + (i / W) * g.Wp + (i % W)) * 8;
+    *reinterpret_cast<uint4*>(gbase + (long long)head * g.PL * 8 + pix) = pack8(dq);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < seq; j += blockDim.x) {
+    float k[8], v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { k[e] = ks[j * 8 + e]; v[e] = vs[j * 8 + e]; }
+    float dk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < seq; ++i) {
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s = fmaf(qs[i * 8 + e], k[e], s); dp = fmaf(ds[i * 8 + e], v[e], dp); }
+      const float P = __expf(s * sc - rm[i]) * rl[i];
+      const float dS = P * (dp - rd[i]) * sc;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { dv[e] = fmaf(P, ds[i * 8 + e], dv[e]); dk[e] = fmaf(dS, qs[i * 8 + e], dk[e]); }
+    }
+    const long long pix = (long long)(g.lead + (j / W) * g.Wp + (j % W)) * 8;
+    *reinterpret_cast<uint4*>(gbase + (long long)(planes + head) * g.PL * 8 + pix) = pack8(dk);
+    *reinterpret_cast<uint4*>(gbase + (long long)(2 * planes + head) * g.PL * 8 + pix) = pack8(dv);
+  }
+}
+cudaError_t launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* go, __nv_bfloat16* gqkv, int N, int C, int H,
+                                 int W, cudaStream_t s) {
+  const int seq = H * W;
+  const size_t smem = (size_t)seq * 35 * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  static size_t smem_set = 48 * 1024;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    smem_set = smem;
+  }
+  const int threads = seq >= 256 ? 256 : ((seq + 31) / 32) * 32;
+  attention_bwd_kernel<<<dim3(C >> 3, N), threads, smem, s>>>(qkv, go, gqkv, N, C, H, W);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight gradient of a conv with ONE scalar-side channel:  dW[c][tap] += sum_{n,p} G[n][c][p] * X[n][p + shift(tap)]
+// G: PF8 bf16 (C channels), X: fp32 [N][H][W] (zero outside the image).  flip: write tap 8 - t (the cout = 1 conv_out, whose
+// weight gradient is sum_p a[c][p + shift] * g_eps[p]).  grid (pixel chunks, planes, N).
+__global__ void __launch_bounds__(GB_THREADS) scalar_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ G,
+                                                                       const float* __restrict__ X, float* __restrict__ dW,
+                                                                       int N, int C, int H, int W, int flip) {
+  __shared__ float red[GB_THREADS / 32][72];
+  const int n = blockIdx.z, pl = blockIdx.y;
+  const Geom g = make_geom(N, H, W);
+  const __nv_bfloat16* gp = G + ((long long)n * (C >> 3) + pl) * g.PL * 8;
+  const float* xi = X + (long long)n * H * W;
+  float acc[8][9];
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[e][t] = 0.f;
+  const int hw = H * W;
+  const int pend = min(hw, (int)(blockIdx.x + 1) * GB_PIX);
+  for (int pidx = blockIdx.x * GB_PIX + threadIdx.x; pidx < pend; pidx += GB_THREADS) {
+    const int h = pidx / W, w = pidx - h * W;
+    float gv[8], xv[9];
+    unpack8(*reinterpret_cast<const uint4*>(gp + (long long)(g.lead + h * g.Wp + w) * 8), gv);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
+      xv[t] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xi + hh * W + ww) : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[e][t] = fmaf(gv[e], xv[t], acc[e][t]);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float a = warp_sum_f(acc[e][t]);
+      if (lane == 0) red[warp][e * 9 + t] = a;
+    }
+  __syncthreads();
+  if (threadIdx.x < 72) {
+    float s = 0.f;
+    for (int k = 0; k < GB_THREADS / 32; ++k) s += red[k][threadIdx.x];
+    const int e = threadIdx.x / 9, t = threadIdx.x - e * 9;
+    atomicAdd(dW + (long long)(pl * 8 + e) * 9 + (flip ? 8 - t : t), s);
+  }
+}
+cudaError_t launch_scalar_conv_wgrad(const __nv_bfloat16* G, const float* X, float* dW, int N, int C, int H, int W, int flip,
+                                     cudaStream_t s) {
+  scalar_conv_wgrad_kernel<<<dim3((H * W + GB_PIX - 1) / GB_PIX, C >> 3, N), GB_THREADS, 0, s>>>(G, X, dW, N, C, H, W, flip);
+  return cudaGetLastError();
+}
+
+// conv_out's data gradient is a cin = 1 convolution of g_eps with the mirrored weights: w'[c][t] = w[c][8 - t]
+__global__ void flip_taps_kernel(const float* __restrict__ w, float* __restrict__ wf, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * 9) return;
+  const int c = i / 9, t = i - c * 9;
+  wf[i] = w[c * 9 + 8 - t];
+}
+cudaError_t launch_flip_taps(const float* w, float* wf, int C, cudaStream_t s) {
+  flip_taps_kernel<<<(C * 9 + 255) / 256, 256, 0, s>>>(w, wf, C);
+  return cudaGetLastError();
+}
+
+// sum of a fp32 array into dst[0] (+=): conv_out bias gradient
+__global__ void __launch_bounds__(256) sum_add_kernel(const float* __restrict__ x, long long n, float* __restrict__ dst) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += x[i];
+  s = warp_sum_f(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    atomicAdd(dst, t);
+  }
+}
+cudaError_t launch_sum_add(const float* x, long long n, float* dst, cudaStream_t s) {
+  const int grid = (int)((n + 2047) / 2048 < 296 ? (n + 2047) / 2048 : 296);
+  sum_add_kernel<<<grid, 256, 0, s>>>(x, n, dst);
+  return cudaGetLastError();
+}
+
+// folded-upsample weight gradient back to the 3x3 taps: dW3[co][ci][k] += sum over (parity p, folded tap t) whose fold mask
+// contains k of dWf[p][co][ci][t]
+__global__ void unfold_up2_kernel(const float* __restrict__ dwf, float* __restrict__ dw3, long long nco_ci, UnfoldMasks m) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nco_ci) return;
+  float a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int p = 0; p < 4; ++p)
+    for (int t = 0; t < 4; ++t) {
+      const float v = dwf[((long long)p * nco_ci + i) * 4 + t];
+      const unsigned mask = m.mask[p][t];
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+        if (mask & (1u << k)) a[k] += v;
+    }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) dw3[i * 9 + k] += a[k];
+}
+cudaError_t launch_unfold_up2(const float* dwf, float* dw3, long long nco_ci, const UnfoldMasks& m, cudaStream_t s) {
+  unfold_up2_kernel<<<(unsigned)((nco_ci + 255) / 256), 256, 0, s>>>(dwf, dw3, nco_ci, m);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Small dense layers of the timestep path.  y[n][o] = sum_i W[o][i] x[n][i] + b[o]
+//   g_in[n][i] (+)= sum_o g[n][o] W[o][i];   dW[o][i] += sum_n g[n][o] x[n][i];   db[o] += sum_n g[n][o]
+__global__ void lin_bwd_input_kernel(const float* __restrict__ g, int gstride, const float* __restrict__ Wt, int O, int I,
+                                     float* __restrict__ gin, int N, int accumulate) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * I) return;
+  const int n = idx / I, i = idx - n * I;
+  float a = 0.f;
+  for (int o = 0; o < O; ++o) a = fmaf(g[(long long)n * gstride + o], Wt[(long long)o * I + i], a);
+  if (accumulate) gin[idx] += a; else gin[idx] = a;
+}
+__global__ void lin_bwd_weight_kernel(const float* __restrict__ g, int gstride, const float* __restrict__ x, int O, int I,
+                                      float* __restrict__ dW, float* __restrict__ db, int N) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= O * I) return;
+  const int o = idx / I, i = idx - o * I;
+  float a = 0.f, b = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float gv = g[(long long)n * gstride + o];
+    a = fmaf(gv, x[(long long)n * I + i], a);
+    b += gv;
+  }
+  dW[idx] += a;
+  if (i == 0 && db) db[o] += b;
+}
+__global__ void silu_bwd_kernel(float* __restrict__ g, const float* __restrict__ u, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float y = u[i];
+  const float sig = 1.0f / (1.0f + expf(-y));
+  g[i] *= sig * (1.0f + y * (1.0f - sig));
+}
+cudaError_t launch_lin_bwd_input(const float* g, int gstride, const float* W, int O, int I, float* gin, int N, int accumulate,
+                                 cudaStream_t s) {
+  lin_bwd_input_kernel<<<(N * I + 127) / 128, 128, 0, s>>>(g, gstride, W, O, I, gin, N, accumulate);
+  return cudaGetLastError();
+}
+cudaError_t launch_lin_bwd_weight(const float* g, int gstride, const float* x, int O, int I, float* dW, float* db, int N,
+                                  cudaStream_t s) {
+  lin_bwd_weight_kernel<<<(O * I + 127) / 128, 128, 0, s>>>(g, gstride, x, O, I, dW, db, N);
+  return cudaGetLastError();
+}
+cudaError_t launch_silu_bwd(float* g, const float* u, int n, cudaStream_t s) {
+  silu_bwd_kernel<<<(n + 255) / 256, 256, 0, s>>>(g, u, n);
+  return cudaGetLastError();
+}
+__global__ void silu_fwd_kernel(const float* __restrict__ u, float* __restrict__ y, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = silu_f(u[i]);
+}
+cudaError_t launch_silu_fwd(const float* u, float* y, int n, cudaStream_t s) {
+  silu_fwd_kernel<<<(n + 255) / 256, 256, 0, s>>>(u, y, n);
+  return cudaGetLastError();
+}
+
+}  // namespace b200ad

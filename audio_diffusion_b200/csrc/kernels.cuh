@@ -107,7 +107,8 @@ cudaError_t launch_pf8_to_nchw(const __nv_bfloat16* src, float* dst, int N, int 
 // then all resnet projections at once: proj [N][rows] = Wcat [rows][4*dim0] * temb_act + bcat.
 cudaError_t launch_temb(const float* t, int N, int dim0, const float* w1, const float* b1, const float* w2,
                         const float* b2, float* temb_act, const float* wcat, const float* bcat, int rows,
-                        float* proj, cudaStream_t s);
+                        float* proj, cudaStream_t s, float* save_emb = nullptr, float* save_u1 = nullptr,
+                        float* save_u2 = nullptr);
 
 // self-attention core on the fused qkv tensor (PF8, 3*C channels: q | k | v; head_dim 8 = one plane per head).
 cudaError_t launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int N, int C, int H, int W, cudaStream_t s);

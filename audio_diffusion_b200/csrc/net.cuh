@@ -97,6 +97,10 @@ struct NetBase {
   size_t stats_bytes = 0;
   float* temb_act = nullptr;
   float* temb_proj = nullptr;
+  bool training = false;            // keep every activation (no pooling) and the timestep-MLP pre-activations for backward
+  float* temb_emb = nullptr;        // [N][dim0]      sinusoid
+  float* temb_u1 = nullptr;         // [N][4 dim0]    linear_1 output before SiLU
+  float* temb_u2 = nullptr;         // [N][4 dim0]    linear_2 output before SiLU
   int num_sms = 148;
   int last_launches = 0;
 };
@@ -453,6 +457,8 @@ struct Builder {
       p.temb = nullptr; p.temb_stride = 0;
       plan->push_back(op);
     }
+    h->taps[n + ".qkv"] = qkv;
+    h->taps[n + ".ao"] = ao;
     h->taps[n] = out;
     return out;
   }

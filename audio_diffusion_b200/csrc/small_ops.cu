@@ -17,7 +17,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 // one CTA per sample: emb[dim0] -> h1[4 dim0] -> temb_act[4 dim0]
 __global__ void __launch_bounds__(256) temb_mlp_kernel(const float* __restrict__ t, int dim0, const float* __restrict__ w1,
                                                        const float* __restrict__ b1, const float* __restrict__ w2,
-                                                       const float* __restrict__ b2, float* __restrict__ temb_act) {
+                                                       const float* __restrict__ b2, float* __restrict__ temb_act,
+                                                       float* __restrict__ save_emb, float* __restrict__ save_u1,
+                                                       float* __restrict__ save_u2) {
   extern __shared__ float tsm[];
   float* emb = tsm;          // dim0
   float* h1 = tsm + dim0;    // 4*dim0
@@ -28,6 +30,7 @@ __global__ void __launch_bounds__(256) temb_mlp_kernel(const float* __restrict__
     const float a = tv * freq;
     emb[i] = cosf(a);          // flip_sin_to_cos: [cos | sin]
     emb[half + i] = sinf(a);
+    if (save_emb) { save_emb[(long long)n * dim0 + i] = emb[i]; save_emb[(long long)n * dim0 + half + i] = emb[half + i]; }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -35,14 +38,20 @@ __global__ void __launch_bounds__(256) temb_mlp_kernel(const float* __restrict__
     float s = 0.f;
     for (int k = lane; k < dim0; k += 32) s += w1[(long long)r * dim0 + k] * emb[k];
     s = warp_sum(s);
-    if (lane == 0) h1[r] = silu_f(s + b1[r]);
+    if (lane == 0) {
+      h1[r] = silu_f(s + b1[r]);
+      if (save_u1) save_u1[(long long)n * D + r] = s + b1[r];
+    }
   }
   __syncthreads();
   for (int r = warp; r < D; r += nw) {
     float s = 0.f;
     for (int k = lane; k < D; k += 32) s += w2[(long long)r * D + k] * h1[k];
     s = warp_sum(s);
-    if (lane == 0) temb_act[(long long)n * D + r] = silu_f(s + b2[r]);
+    if (lane == 0) {
+      temb_act[(long long)n * D + r] = silu_f(s + b2[r]);
+      if (save_u2) save_u2[(long long)n * D + r] = s + b2[r];
+    }
   }
 }
 
@@ -67,10 +76,10 @@ __global__ void __launch_bounds__(256) temb_proj_kernel(const float* __restrict_
 
 cudaError_t launch_temb(const float* t, int N, int dim0, const float* w1, const float* b1, const float* w2,
                         const float* b2, float* temb_act, const float* wcat, const float* bcat, int rows,
-                        float* proj, cudaStream_t s) {
+                        float* proj, cudaStream_t s, float* save_emb, float* save_u1, float* save_u2) {
   const int D = 4 * dim0;
   if (D > 1024 || (D % 32) != 0) return cudaErrorInvalidValue;
-  temb_mlp_kernel<<<N, 256, (dim0 + D) * sizeof(float), s>>>(t, dim0, w1, b1, w2, b2, temb_act);
+  temb_mlp_kernel<<<N, 256, (dim0 + D) * sizeof(float), s>>>(t, dim0, w1, b1, w2, b2, temb_act, save_emb, save_u1, save_u2);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   temb_proj_kernel<<<(rows + 7) / 8, 256, 0, s>>>(temb_act, N, D, wcat, bcat, rows, proj);

@@ -1,7 +1,7 @@
 // Host side of the U-Net: parameter table (diffusers naming), weight packing, activation workspace layout and
 // the launch plan that walks UNet2DModel.forward (reference call sites: audiodiffusion/pipeline_audio_diffusion.py:163,
 // :237; architecture: scripts/train_unet.py:115-137).  No tensor math happens on the host.
-#include "net.cuh"
+#include "unet.cuh"
 
 namespace b200ad {
 
@@ -18,9 +18,6 @@ int set_err(const char* fmt, ...) {
 
 using namespace b200ad;
 
-struct b200ad_unet : NetBase {
-  b200ad_unet_config cfg;
-};
 
 namespace b200ad {
 
@@ -184,7 +181,7 @@ static int build_plan(b200ad_unet* h, uint8_t* ws_base, int N, int H, int W, siz
   B.h = h; B.N = N; B.plan = &plan;
   {
     const char* e = getenv("B200AD_DEBUG_NOPOOL");
-    B.nopool = e && e[0] == '1';
+    B.nopool = (e && e[0] == '1') || h->training;
   }
   B.ws.base = ws_base;
   // two-pass: the stats arena lives at the start of the workspace; its size is found by a dry run
@@ -201,6 +198,11 @@ static int build_plan(b200ad_unet* h, uint8_t* ws_base, int N, int H, int W, siz
     const int D = c.block_out_channels[0] * 4;
     h->temb_act = (float*)B.ws.take((size_t)N * D * 4);
     h->temb_proj = (float*)B.ws.take((size_t)N * h->temb_rows * 4);
+    if (h->training) {
+      h->temb_emb = (float*)B.ws.take((size_t)N * c.block_out_channels[0] * 4);
+      h->temb_u1 = (float*)B.ws.take((size_t)N * D * 4);
+      h->temb_u2 = (float*)B.ws.take((size_t)N * D * 4);
+    }
     {
       Op op{};
       op.kind = OP_TEMB;
@@ -236,6 +238,7 @@ static int build_plan(b200ad_unet* h, uint8_t* ws_base, int N, int H, int W, siz
         const Geom go = make_geom(N, Ho, Wo);
         const size_t tsz = (size_t)N * (out_c / 8) * go.PL * 8;  // elements per parity tensor
         Act par = B.pooled("parity", 4 * out_c, Ho, Wo, false);  // 4 tensors back to back (same bytes as 4C channels)
+        h->taps[n + ".parity"] = par;
         {
           Op op{};
           op.kind = OP_PARITY;
@@ -345,12 +348,14 @@ extern "C" size_t b200ad_unet_workspace_bytes(const b200ad_unet* hc, int N, int 
   auto saved_plan = h->plan;
   auto saved_taps = h->taps;
   stat_t* sa = h->stats_arena; size_t sb = h->stats_bytes; float* ta = h->temb_act; float* tp = h->temb_proj;
+  float* te = h->temb_emb; float* tu1 = h->temb_u1; float* tu2 = h->temb_u2;
   uint8_t* saved_packed = h->packed;
   std::vector<const float*> saved_pptr = h->pptr;
   size_t bytes = 0;
   build_plan(h, nullptr, N, H, W, &bytes);
   h->plan = saved_plan; h->taps = saved_taps; h->stats_arena = sa; h->stats_bytes = sb; h->temb_act = ta; h->temb_proj = tp;
   h->packed = saved_packed; h->pptr = saved_pptr;
+  h->temb_emb = te; h->temb_u1 = tu1; h->temb_u2 = tu2;
   return bytes;
 }
 
@@ -386,7 +391,8 @@ static int run_plan(b200ad_unet* h, const float* x, const float* t, const float*
                        h->pptr[h->pidx.at("time_embedding.linear_2.weight")],
                        h->pptr[h->pidx.at("time_embedding.linear_2.bias")], h->temb_act,
                        (const float*)(h->packed + h->off_wcat), (const float*)(h->packed + h->off_bcat), h->temb_rows,
-                       h->temb_proj, st));
+                       h->temb_proj, st, h->training ? h->temb_emb : nullptr, h->training ? h->temb_u1 : nullptr,
+                       h->training ? h->temb_u2 : nullptr));
         launches += 2;
         break;
       }

@@ -41,6 +41,24 @@ def _set_deep(root: nn.Module, dotted: str, p: nn.Parameter) -> None:
     m.register_parameter(parts[-1], p)
 
 
+class _UNetFunction(torch.autograd.Function):
+    """Autograd node of the training forward: the backward pass is `b200ad_unet_backward` (all parameter gradients in one
+    call); the gradient w.r.t. the input sample is not produced (the reference never needs it)."""
+
+    @staticmethod
+    def forward(ctx, model, x, t, *params):
+        out = model._forward_train(x, t)
+        ctx.model = model
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        grads = ctx.model._backward_train(x, g)
+        return (None, None, None) + tuple(gr.clone() for gr in grads)
+
+
 class UNet2DModel(nn.Module):
     def __init__(
         self,
@@ -199,12 +217,18 @@ class UNet2DModel(nn.Module):
     # ------------------------------------------------------------------ public call
     def forward(self, sample: torch.Tensor, timestep, return_dict: bool = True):
         """ε = unet(sample, timestep)["sample"] — pipeline_audio_diffusion.py:163."""
-        if sample.requires_grad or (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-                                    and self.training):
-            raise NotImplementedError("UNet2DModel(b200): the backward pass is not built yet (inference only)")
+        if sample.requires_grad:
+            raise NotImplementedError("UNet2DModel(b200): gradients w.r.t. the input sample are not computed")
+        needs_grad = torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters())
         x = self._check_input(sample)
         n, _, hh, ww = x.shape
+        if needs_grad:      # training step (scripts/train_unet.py:257-259): forward keeps every activation, backward in CUDA
+            t = self._timesteps(timestep, n, x.device)
+            named = self._named()
+            out = _UNetFunction.apply(self, x, t, *[named[k] for k in self._pnames])
+            return UNet2DOutput(out) if return_dict else (out,)
         with torch.cuda.device(x.device):
+            self._set_training_mode(False)
             self._ensure_bound(n, hh, ww)
             t = self._timesteps(timestep, n, x.device)
             out = torch.empty((n, self.out_channels, hh, ww), dtype=torch.float32, device=x.device)
@@ -214,6 +238,54 @@ class UNet2DModel(nn.Module):
             return (out,)
         return UNet2DOutput(out)
 
+    # ------------------------------------------------------------------ training (backward in libb200ad)
+    def _set_training_mode(self, on: bool) -> None:
+        if getattr(self, "_train_mode", False) != on:
+            _lib.check(_lib.lib().b200ad_unet_set_training(self._h, 1 if on else 0))
+            self._train_mode = on
+            self._ws_key = None        # the workspace layout differs (no buffer pooling when training)
+            self._bwd_key = None
+
+    def _forward_train(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        L = _lib.lib()
+        n, _, hh, ww = x.shape
+        with torch.cuda.device(x.device):
+            self._set_training_mode(True)
+            self._ensure_bound(n, hh, ww)
+            if getattr(self, "_bwd_key", None) != self._ws_key:
+                nfl = L.b200ad_unet_grad_floats(self._h)
+                if getattr(self, "_grad_flat", None) is None or self._grad_flat.numel() != nfl or self._grad_flat.device != x.device:
+                    self._grad_flat = torch.zeros(nfl, dtype=torch.float32, device=x.device)
+                need = L.b200ad_unet_backward_bytes(self._h)
+                if need == 0:
+                    _lib.check(-1)
+                if getattr(self, "_bwd_arena", None) is None or self._bwd_arena.numel() < need or self._bwd_arena.device != x.device:
+                    self._bwd_arena = None
+                    self._bwd_arena = torch.empty(need, dtype=torch.uint8, device=x.device)
+                _lib.check(L.b200ad_unet_bind_backward(self._h, self._bwd_arena.data_ptr(), self._bwd_arena.numel(),
+                                                       self._grad_flat.data_ptr(), _lib.stream_ptr()))
+                self._bwd_key = self._ws_key
+            out = torch.empty((n, self.out_channels, hh, ww), dtype=torch.float32, device=x.device)
+            _lib.check(L.b200ad_unet_forward(self._h, x.data_ptr(), t.data_ptr(), out.data_ptr(), _lib.stream_ptr()))
+        return out
+
+    def _backward_train(self, x: torch.Tensor, g: torch.Tensor):
+        L = _lib.lib()
+        g = g.to(torch.float32).contiguous()
+        with torch.cuda.device(x.device):
+            _lib.check(L.b200ad_unet_backward(self._h, x.data_ptr(), g.data_ptr(), _lib.stream_ptr()))
+        named = self._named()
+        grads = []
+        for i, k in enumerate(self._pnames):
+            off = L.b200ad_unet_grad_offset(self._h, i)
+            p = named[k]
+            grads.append(self._grad_flat[off:off + p.numel()].view(p.shape))
+        return grads
+
+    @property
+    def last_backward_launch_count(self) -> int:
+        return _lib.lib().b200ad_unet_backward_launch_count(self._h)
+
     @torch.no_grad()
     def forward_step(self, sample: torch.Tensor, timestep, coef: StepCoefC, noise: Optional[torch.Tensor] = None,
                      out: Optional[torch.Tensor] = None, want_eps: bool = False):
@@ -221,6 +293,7 @@ class UNet2DModel(nn.Module):
         x = self._check_input(sample)
         n, _, hh, ww = x.shape
         with torch.cuda.device(x.device):
+            self._set_training_mode(False)
             self._ensure_bound(n, hh, ww)
             t = self._timesteps(timestep, n, x.device)
             if out is None:

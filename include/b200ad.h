@@ -92,6 +92,19 @@ int b200ad_unet_profile_step(b200ad_unet* h, const float* x, const float* t, con
 /* Number of kernel launches the last forward enqueued. */
 int b200ad_unet_last_launch_count(const b200ad_unet* h);
 
+/* ---- U-Net backward (scripts/train_unet.py:259 `accelerator.backward(loss)`) ----------------------------
+ * Protocol: set_training(1) -> bind_workspace (every activation is kept) -> bind_backward -> per step: forward(x, t),
+ * then backward(x, dL/d eps). Parameter gradients land in ONE flat fp32 buffer (zeroed by backward()); parameter i of the
+ * table lives at float offset b200ad_unet_grad_offset(h, i) — the Python mirror exposes them as `p.grad` views. */
+int b200ad_unet_set_training(b200ad_unet* h, int on);
+size_t b200ad_unet_grad_floats(b200ad_unet* h);
+size_t b200ad_unet_grad_offset(b200ad_unet* h, int i);
+size_t b200ad_unet_backward_bytes(b200ad_unet* h);       /* arena for activation gradients, temporaries, transposed weights */
+int b200ad_unet_bind_backward(b200ad_unet* h, void* arena, size_t bytes, float* grads, void* stream);
+/* x: the forward input [N, 1, H, W]; g_eps: gradient of the loss w.r.t. the forward output, fp32 [N, 1, H, W]. */
+int b200ad_unet_backward(b200ad_unet* h, const float* x, const float* g_eps, void* stream);
+int b200ad_unet_backward_launch_count(const b200ad_unet* h);
+
 /* ---- Latent autoencoder: replaces diffusers.AutoencoderKL as the pipeline drives it ---------------------
  * (audiodiffusion/pipeline_audio_diffusion.py:143-147 encode + sample, :187-190 decode; architecture
  * config/ldm_autoencoder_kl.yaml:18-28; state-dict keys as audiodiffusion/utils.py:156-303 produces them). */
@@ -169,6 +182,12 @@ int b200ad_gn_conv2d(const float* x, const float* gamma, const float* beta, int 
  * same tcgen05 kernel with transposed / mirrored weight packing. cin % 128 == 0, cout % 16 == 0;
  * scratch >= b200ad_conv2d_scratch_bytes(N, cout, cin, H, W, K, 1). */
 int b200ad_conv2d_dgrad(const float* gy, const float* w, float* gx, int N, int cin, int cout, int H, int W, int K,
+                        void* scratch, size_t scratch_bytes, void* stream);
+/* Weight gradient of the same conv (autograd's conv2d backward for the weight): gy [N, cout, H, W], a [N, cin, H, W] (the
+ * conv's input) -> dw fp32 [cout, cin, K, K] (overwritten). tcgen05 with pixels as the reduction dimension (both operands
+ * MN-major); cout % 128 == 0, cin % 32 == 0. */
+size_t b200ad_conv2d_wgrad_scratch_bytes(int N, int cin, int cout, int H, int W);
+int b200ad_conv2d_wgrad(const float* gy, const float* a, float* dw, int N, int cin, int cout, int H, int W, int K,
                         void* scratch, size_t scratch_bytes, void* stream);
 /* GroupNorm(groups, eps) [+ SiLU] on fp32 NCHW through the stats + apply kernels. */
 int b200ad_group_norm(const float* x, const float* gamma, const float* beta, float* y, int N, int C, int H, int W,
