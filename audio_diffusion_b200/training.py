@@ -171,6 +171,8 @@ class FusedAdamW(torch.optim.Optimizer):
         arr = (C.c_void_p * len(grads))(*[t.data_ptr() for t in grads])
         with torch.cuda.device(ps[0].device):
             _lib.check(_lib.lib().b200ad_optim_step(self._h, arr, C.byref(hp), self.grad_norm.data_ptr(), _lib.stream_ptr()))
+        for p in ps:      # the kernel wrote through raw pointers: tell autograd (and the U-Net's weight-packing cache) so
+            torch.autograd.graph.increment_version(p)
         return loss
 
 
