@@ -368,10 +368,10 @@ struct BwdBuilder {
         op.conv.nseg = 1;
         bw->ops.push_back(op);
       }
-    if (const __nv_bfloat16* sk = skip_of(xn)) {
+    if (skipgrad.count(xn)) {
       BOp op{};
       op.kind = BOp::PF8ADD;
-      op.dst = Gx.p; op.src = sk; op.C = C; op.H = x.H; op.W = x.W;
+      op.dst = Gx.p; op.src = skip_of(xn); op.C = C; op.H = x.H; op.W = x.W;
       bw->ops.push_back(op);
     }
   }
@@ -548,7 +548,7 @@ static int build_backward(b200ad_unet* h, Backward* bw, uint8_t* arena, float* g
     if (c.in_channels != 1) return set_err("backward: in_channels != 1 is not implemented");
     const Act x = h->taps.at("conv_in");
     const Act Gx = B.G("conv_in");
-    if (B.skip_of("conv_in") == nullptr) return set_err("backward: conv_in skip gradient missing");
+    if (!B.skipgrad.count("conv_in")) return set_err("backward: conv_in skip gradient missing");
     // (the first resnet's GroupNorm backward already added the skip contribution)
     BOp w{};
     w.kind = BOp::SCALAR_WGRAD;
