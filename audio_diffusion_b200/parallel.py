@@ -32,3 +32,15 @@ def shard_noise(global_shape: Sequence[int], generator: torch.Generator, rank: i
     (pipeline_audio_diffusion.py:120-130) made once for the GLOBAL batch."""
     full = torch.randn(tuple(global_shape), generator=generator, device=device)
     return full[shard_rows(global_shape[0], rank, world)].contiguous()
+
+
+def allreduce_mean_(flat: torch.Tensor) -> torch.Tensor:
+    """Data-parallel training (scripts/train_unet.py:181,259 — accelerate's DDP): ONE all-reduce of the flat gradient
+    buffer (113.67 M fp32 for the reference U-Net; NCCL over NVLink on GPUs, gloo in the CPU tests), then the mean.
+    No-op without an initialised process group or with a single rank."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return flat
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(dist.get_world_size())
+    return flat

@@ -176,6 +176,31 @@ class FusedAdamW(torch.optim.Optimizer):
         return loss
 
 
+def train_step(model, optimizer: "FusedAdamW", noise_scheduler, clean_images: torch.Tensor, ema: Optional[EMAModel] = None,
+               lr_scheduler=None, generator: Optional[torch.Generator] = None, noise: Optional[torch.Tensor] = None,
+               timesteps: Optional[torch.Tensor] = None):
+    """One iteration of the training loop body, scripts/train_unet.py:238-267, on the engine: noise + per-sample timesteps,
+    `add_noise`, U-Net forward, MSE, backward (CUDA), clip + AdamW + EMA (one fused kernel pass), LR scheduler step.
+    Returns the loss tensor (detached).  `noise` / `timesteps` may be given for reproducible tests."""
+    x = clean_images
+    if noise is None:
+        noise = torch.randn(x.shape, generator=generator, device=x.device if generator is None else generator.device).to(x.device)
+    if timesteps is None:
+        timesteps = torch.randint(0, noise_scheduler.config.num_train_timesteps, (x.shape[0],), generator=generator,
+                                  device=x.device if generator is None else generator.device).long().to(x.device)
+    noisy = noise_scheduler.add_noise(x, noise, timesteps)
+    pred = model(noisy, timesteps)["sample"]
+    loss = torch.nn.functional.mse_loss(pred, noise)
+    loss.backward()
+    optimizer.step()
+    if lr_scheduler is not None:
+        lr_scheduler.step()
+    if ema is not None:
+        ema.step(model.parameters())
+    optimizer.zero_grad(set_to_none=True)
+    return loss.detach()
+
+
 def mse_loss(pred: torch.Tensor, target: torch.Tensor, want_grad: bool = True):
     """(`F.mse_loss(pred, target)`, dL/dpred) — train_unet.py:258 and the seed of the backward pass."""
     _lib.require_cuda()

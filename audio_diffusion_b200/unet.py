@@ -274,6 +274,8 @@ class UNet2DModel(nn.Module):
         g = g.to(torch.float32).contiguous()
         with torch.cuda.device(x.device):
             _lib.check(L.b200ad_unet_backward(self._h, x.data_ptr(), g.data_ptr(), _lib.stream_ptr()))
+        from .parallel import allreduce_mean_
+        allreduce_mean_(self._grad_flat)          # data parallel: one collective over the flat gradient buffer
         named = self._named()
         grads = []
         for i, k in enumerate(self._pnames):

@@ -169,3 +169,27 @@ print('OK', len(sd))
 """
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "OK 248" in r.stdout, r.stdout + r.stderr
+
+
+def test_gradient_allreduce_gloo_world2():
+    """Data-parallel training's host logic (scripts/train_unet.py:181,259 via accelerate DDP): one all-reduce of the flat
+    gradient buffer, mean over ranks — over gloo with world_size 2 (NCCL on the GPU box)."""
+    code = f"""
+import os, sys
+sys.path.insert(0, {ROOT!r})
+import torch, torch.distributed as dist
+from audio_diffusion_b200.parallel import allreduce_mean_
+rank = int(os.environ['RANK'])
+dist.init_process_group('gloo', rank=rank, world_size=2)
+flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+allreduce_mean_(flat)
+assert torch.equal(flat, torch.arange(1000, dtype=torch.float32) * 1.5), flat[:4]
+dist.destroy_process_group()
+print('OK', rank)
+"""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29617", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, "-c", code], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0 and "OK" in o, o + e
