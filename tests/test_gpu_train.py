@@ -173,3 +173,37 @@ def test_two_training_steps_match_oracle(cuda):
                    for s, k in zip(ema.shadow_params, names)) / total
     print("fraction within 10% of the update scale:", frac, frac_ema)
     assert frac >= 0.99 and frac_ema >= 0.99, (frac, frac_ema)
+
+
+@pytest.mark.timeout(900)
+def test_unet_backward_reference_architecture(cuda):
+    """Same gradient parity on the architecture the reference trains (scripts/train_unet.py:115-137: six levels, attention in
+    down block 4 / up block 1, 113.67 M parameters) at 64x64, batch 1 — every block type at every depth, 2x2 bottleneck."""
+    from audio_diffusion_b200.unet import UNet2DModel
+    from oracle.schedulers_oracle import OracleDDPM
+    from oracle.train_oracle import loss_and_grads
+    from oracle.unet_oracle import UNetConfig, init_weights
+    full = dict(in_channels=1, out_channels=1, layers_per_block=2, block_out_channels=(128, 128, 256, 256, 512, 512),
+                down_block_types=("DownBlock2D",) * 4 + ("AttnDownBlock2D", "DownBlock2D"),
+                up_block_types=("UpBlock2D", "AttnUpBlock2D", "UpBlock2D", "UpBlock2D", "UpBlock2D", "UpBlock2D"))
+    ocfg = UNetConfig(sample_size=(64, 64), **full)
+    w = init_weights(ocfg, seed=7)
+    model = UNet2DModel(sample_size=(64, 64), **full)
+    model.load_state_dict(w)
+    model = model.to(cuda).train()
+    g = torch.Generator().manual_seed(8)
+    clean = torch.rand(1, 1, 64, 64, generator=g) * 2 - 1
+    noise = torch.randn(1, 1, 64, 64, generator=g)
+    t = torch.tensor([500])
+    loss_ref, grads_ref, _ = loss_and_grads(w, ocfg, clean, noise, t)
+    noisy = OracleDDPM().add_noise(clean, noise, t).to(cuda)
+    pred = model(noisy, t.to(cuda))["sample"]
+    torch.nn.functional.mse_loss(pred, noise.to(cuda)).backward()
+    torch.cuda.synchronize()
+    rows, total = _grad_report(model, grads_ref)
+    for e, k, s, gn in rows[:12]:
+        print(f"{e:9.4f}  |ref| {s:10.3e}  |got| {gn:10.3e}  {k}")
+    print("total relative L2 error", total)
+    gmax = max(r[2] for r in rows)
+    bad = [(e, k) for e, k, s, _ in rows if e > 0.10 and s > 1e-3 * gmax]
+    assert total <= 3e-2 and not bad, (total, bad[:10])
