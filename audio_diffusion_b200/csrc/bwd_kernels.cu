@@ -500,14 +500,16 @@ cudaError_t launch_unfold_up2(const float* dwf, float* dw3, long long nco_ci, co
 // ---------------------------------------------------------------------------------------------------------------------
 // Small dense layers of the timestep path.  y[n][o] = sum_i W[o][i] x[n][i] + b[o]
 //   g_in[n][i] (+)= sum_o g[n][o] W[o][i];   dW[o][i] += sum_n g[n][o] x[n][i];   db[o] += sum_n g[n][o]
+constexpr int LIN_OCHUNK = 128;   // output rows per CTA along grid.y (partial sums combined with atomics)
 __global__ void lin_bwd_input_kernel(const float* __restrict__ g, int gstride, const float* __restrict__ Wt, int O, int I,
-                                     float* __restrict__ gin, int N, int accumulate) {
+                                     float* __restrict__ gin, int N) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * I) return;
   const int n = idx / I, i = idx - n * I;
+  const int o1 = min(O, (int)(blockIdx.y + 1) * LIN_OCHUNK);
   float a = 0.f;
-  for (int o = 0; o < O; ++o) a = fmaf(g[(long long)n * gstride + o], Wt[(long long)o * I + i], a);
-  if (accumulate) gin[idx] += a; else gin[idx] = a;
+  for (int o = blockIdx.y * LIN_OCHUNK; o < o1; ++o) a = fmaf(g[(long long)n * gstride + o], Wt[(long long)o * I + i], a);
+  atomicAdd(gin + idx, a);
 }
 __global__ void lin_bwd_weight_kernel(const float* __restrict__ g, int gstride, const float* __restrict__ x, int O, int I,
                                       float* __restrict__ dW, float* __restrict__ db, int N) {
@@ -532,7 +534,11 @@ __global__ void silu_bwd_kernel(float* __restrict__ g, const float* __restrict__
 }
 cudaError_t launch_lin_bwd_input(const float* g, int gstride, const float* W, int O, int I, float* gin, int N, int accumulate,
                                  cudaStream_t s) {
-  lin_bwd_input_kernel<<<(N * I + 127) / 128, 128, 0, s>>>(g, gstride, W, O, I, gin, N, accumulate);
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(gin, 0, (size_t)N * I * sizeof(float), s);
+    if (e != cudaSuccess) return e;
+  }
+  lin_bwd_input_kernel<<<dim3((N * I + 127) / 128, (O + LIN_OCHUNK - 1) / LIN_OCHUNK), 128, 0, s>>>(g, gstride, W, O, I, gin, N);
   return cudaGetLastError();
 }
 cudaError_t launch_lin_bwd_weight(const float* g, int gstride, const float* x, int O, int I, float* dW, float* db, int N,

@@ -76,33 +76,43 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, WG_NCI) | (1u << 15) | (1u << 16);   // A and B MN-major
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t first = 1;
-      for (int b = blockIdx.x; b < total_blocks; b += gridDim.x) {
-        mbar_wait(bar_full + 8 * stage, phase);
-        tc_fence_after();
-        const uint32_t a0 = smem_base + stage * stage_bytes;
-        const uint32_t b0 = a0 + gy_bytes;
-        const uint32_t sbo_a = (uint32_t)p.P * 16u, sbo_b = (uint32_t)act_pix * 16u;
-        for (int k = 0; k < p.P / 16; ++k) {
-          // MN-major, no swizzle: LBO = distance of the next 8 pixels (K) = 128 B, SBO = distance of the next 8 channels
-          // (MN) = one plane of the staged window  [verified on hardware: tools/wgrad_probe.py]
-          const uint64_t adesc = make_smem_desc(a0 + k * 256, 128, sbo_a);
-          for (int t = 0; t < p.ntaps; ++t) {
-            const uint32_t bs = b0 + (uint32_t)(k * 16 + p.halo + p.shift[t]) * 16u;
-            const uint64_t bdesc = make_smem_desc(bs, 128, sbo_b);
-            umma_bf16(tmem_base + (uint32_t)t * WG_NCI, adesc, bdesc, idesc, (first && k == 0) ? 0u : 1u);
+    // MMA issuer: the warp runs convergently (operands in uniform registers, waits exit on a vote), one elected lane issues.
+    // Per 16 pixels: the gY block (A, 128 co x 16 px) is latched in the A collector and reused by all taps.
+    const uint32_t idesc = make_idesc_bf16(128, WG_NCI) | (1u << 15) | (1u << 16);   // A and B MN-major
+    // MN-major, no swizzle: LBO = distance of the next 8 pixels (K) = 128 B, SBO = distance of the next 8 channels (MN) =
+    // one plane of the staged window  [verified on hardware: tools/wgrad_probe.py]
+    const uint64_t a_hi = (uint64_t)(((uint32_t)p.P & 0x3FFF) | (1u << 14)) << 32;          // SBO = P * 16 B, version 1
+    const uint64_t b_hi = (uint64_t)(((uint32_t)act_pix & 0x3FFF) | (1u << 14)) << 32;
+    constexpr uint32_t lbo = (128u >> 4) << 16;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t first = 1;
+    for (int b = blockIdx.x; b < total_blocks; b += gridDim.x) {
+      mbar_wait_warp(bar_full + 8 * stage, phase);
+      tc_fence_after();
+      const uint32_t a16 = (smem_base + stage * stage_bytes) >> 4;
+      const uint32_t b16 = a16 + ((uint32_t)gy_bytes >> 4) + (uint32_t)p.halo;
+      const int ksteps = p.P / 16, ntaps = p.ntaps;
+      if (elect_one()) {
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t adesc = a_hi | (uint64_t)((a16 + (uint32_t)k * 16u) | lbo);
+          const uint32_t acc = (first && k == 0) ? 0u : 1u;
+          for (int t = 0; t < ntaps; ++t) {
+            const uint64_t bdesc = b_hi | (uint64_t)((b16 + (uint32_t)(k * 16 + p.shift[t])) | lbo);
+            const uint32_t d = tmem_base + (uint32_t)t * WG_NCI;
+            if (ntaps == 1) umma_bf16(d, adesc, bdesc, idesc, acc);
+            else if (t == 0) umma_bf16_afill(d, adesc, bdesc, idesc, acc);
+            else if (t == ntaps - 1) umma_bf16_alast(d, adesc, bdesc, idesc, acc);
+            else umma_bf16_ause(d, adesc, bdesc, idesc, acc);
           }
         }
-        first = 0;
-        umma_commit(bar_empty + 8 * stage);
-        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(bar_done);
+      __syncwarp();
+      first = 0;
+      umma_commit_elect(bar_empty + 8 * stage);
+      if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
     }
+    umma_commit_elect(bar_done);
   } else {
     // epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 = output channels; 32 columns = the CTA's input channels
     const int q = warp & 3;
@@ -143,7 +153,11 @@ cudaError_t launch_wgrad_tc(const WgradDesc& d, int num_sms, cudaStream_t s) {
     if (a > p.halo) p.halo = a;
   }
   if (p.halo > g.lead - 1) return cudaErrorInvalidValue;   // the window may not start before the plane
-  p.P = 128;
+  // pixels per staged block: 256 when two stages fit (fewer, larger bulk copies per pixel), else 128
+  p.P = 256;
+  if ((size_t)WG_STAGES * ((256 * 256 + (WG_NCI / 8) * (256 + 2 * p.halo) * 16 + 127) & ~127) + 256 > (size_t)CONV_SMEM_MAX ||
+      d.H * g.Wp <= 128)
+    p.P = 128;
   p.nblk = (d.H * g.Wp + p.P - 1) / p.P;
   const int act_pix = p.P + 2 * p.halo;
   const int stage_bytes = (p.P * 256 + (WG_NCI / 8) * act_pix * 16 + 127) & ~127;
