@@ -663,11 +663,21 @@ extern "C" int b200ad_unet_backward(b200ad_unet* h, const float* x, const float*
   cudaStream_t st = (cudaStream_t)stream;
   const int N = h->N;
   int launches = 0;
+  // B200AD_BWD_PROFILE=1: CUDA events around every op, per-kind totals printed to stderr (tools/train_bench.py)
+  static const bool prof = [] { const char* e = getenv("B200AD_BWD_PROFILE"); return e && e[0] == '1'; }();
+  std::vector<cudaEvent_t> ev;
+  if (prof) {
+    ev.resize(bw->ops.size() + 2);
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    CK(cudaEventRecord(ev[0], st));
+  }
   CK(cudaMemsetAsync(bw->grads, 0, bw->grad_floats * sizeof(float), st));
   for (const PackJob& j : bw->jobs)
     CK(launch_pack_weights(h->pptr[j.w_param], j.cout, j.cin_total, j.KH, j.KW, j.cin_off, j.ksteps, j.taps,
                            (__nv_bfloat16*)(bw->arena + j.off), st, j.cout_real));
   launches += (int)bw->jobs.size();
+  if (prof) CK(cudaEventRecord(ev[1], st));
+  size_t opi = 0;
   for (BOp& op : bw->ops) {
     switch (op.kind) {
       case BOp::CONV: CK(launch_conv_tc(op.conv, h->num_sms, st)); break;
@@ -696,8 +706,30 @@ extern "C" int b200ad_unet_backward(b200ad_unet* h, const float* x, const float*
       case BOp::MEMSET: CK(cudaMemsetAsync(op.o0, 0, (size_t)op.n, st)); break;
     }
     ++launches;
+    if (prof) CK(cudaEventRecord(ev[2 + opi], st));
+    ++opi;
   }
   bw->launches = launches;
+  if (prof) {
+    static const char* names[] = {"conv_tc(dgrad)", "wgrad_tc", "gn_bwd", "gn_apply", "chan_sum", "reduce_n", "scatter",
+                                  "pf8_add", "attention_bwd", "parity_split", "unfold_up2", "scalar_wgrad", "conv_in(dgrad)",
+                                  "flip", "sum_add", "lin_in", "lin_w", "silu_bwd", "silu_fwd", "memset"};
+    CK(cudaStreamSynchronize(st));
+    double tot[20] = {0};
+    int cnt[20] = {0};
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+    fprintf(stderr, "{\"backward_profile_ms\": {\"pack_transposed\": %.3f", ms);
+    for (size_t i = 0; i < bw->ops.size(); ++i) {
+      CK(cudaEventElapsedTime(&ms, ev[1 + i], ev[2 + i]));
+      tot[bw->ops[i].kind] += ms;
+      cnt[bw->ops[i].kind]++;
+    }
+    for (int k = 0; k < 20; ++k)
+      if (cnt[k]) fprintf(stderr, ", \"%s x%d\": %.3f", names[k], cnt[k], tot[k]);
+    fprintf(stderr, "}}\n");
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
   return 0;
 }
 

@@ -55,8 +55,8 @@ class _UNetFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (x,) = ctx.saved_tensors
-        grads = ctx.model._backward_train(x, g)
-        return (None, None, None) + tuple(gr.clone() for gr in grads)
+        ctx.model._backward_train(x, g)          # fills p.grad (views of the flat gradient buffer)
+        return (None, None, None) + (None,) * len(ctx.model._pnames)
 
 
 class UNet2DModel(nn.Module):
@@ -276,13 +276,21 @@ class UNet2DModel(nn.Module):
             _lib.check(L.b200ad_unet_backward(self._h, x.data_ptr(), g.data_ptr(), _lib.stream_ptr()))
         from .parallel import allreduce_mean_
         allreduce_mean_(self._grad_flat)          # data parallel: one collective over the flat gradient buffer
-        named = self._named()
-        grads = []
-        for i, k in enumerate(self._pnames):
-            off = L.b200ad_unet_grad_offset(self._h, i)
-            p = named[k]
-            grads.append(self._grad_flat[off:off + p.numel()].view(p.shape))
-        return grads
+        # Parameter gradients are VIEWS of the flat buffer, assigned directly (no 700-tensor clone / accumulate pass): the
+        # reference zeroes gradients every iteration (train_unet.py:267); gradient_accumulation_steps > 1 is not supported.
+        if getattr(self, "_grad_views_key", None) != self._grad_flat.data_ptr():
+            named = self._named()
+            self._grad_views = []
+            for i, k in enumerate(self._pnames):
+                off = L.b200ad_unet_grad_offset(self._h, i)
+                p = named[k]
+                self._grad_views.append((p, self._grad_flat[off:off + p.numel()].view(p.shape)))
+            self._grad_views_key = self._grad_flat.data_ptr()
+        for p, gv in self._grad_views:
+            if p.grad is not None and p.grad.data_ptr() != gv.data_ptr():
+                raise _lib.B200ADError("UNet2DModel(b200): gradient accumulation across backward calls is not supported; "
+                                       "call optimizer.zero_grad(set_to_none=True) every iteration")
+            p.grad = gv
 
     @property
     def last_backward_launch_count(self) -> int:
