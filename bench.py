@@ -306,8 +306,81 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ training mode (extra)
+def run_train(args):
+    """`--mode train`: one iteration of scripts/train_unet.py:238-267 per step (config C5 of SURVEY §8: 256x256, bf16
+    activations, data parallel). Not the headline metric — a separate JSON line with its own metric name."""
+    rank, world, local = dist_env()
+    from audio_diffusion_b200 import _lib
+    from audio_diffusion_b200.parallel import broadcast_parameters
+    from audio_diffusion_b200.schedulers import DDPMScheduler
+    from audio_diffusion_b200.training import EMAModel, FusedAdamW, train_step
+    from audio_diffusion_b200.unet import UNet2DModel
+    _lib.require_cuda()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch if args.batch != 64 else 16          # per-GPU batch (C5 states it): default 16
+    HW = args.res
+    model = UNet2DModel(sample_size=(HW, HW), seed=0, **REF_ARCH).to(dev).train()
+    if use_dist:
+        broadcast_parameters(model.parameters(), src=0)
+    opt = FusedAdamW(model.parameters(), lr=1e-4, betas=(0.95, 0.999), weight_decay=1e-6, eps=1e-8, max_grad_norm=1.0)
+    ema = EMAModel(model.parameters(), inv_gamma=1.0, power=0.75, max_value=0.9999)
+    opt.attach_ema(ema)
+    sch = DDPMScheduler()
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    # synthetic dataset batch: uint8 images through ToTensor + Normalize(.5, .5) (train_unet.py:73-78), resident on the GPU
+    x = (torch.randint(0, 256, (B, 1, HW, HW), device=dev, generator=gen).float() / 255.0 - 0.5) / 0.5
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        train_step(model, opt, sch, x, ema=ema, generator=gen)
+    torch.cuda.synchronize()
+    if use_dist:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = train_step(model, opt, sch, x, ema=ema, generator=gen)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    ms_t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if use_dist:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    ms = ms_t.item()
+    if rank == 0:
+        peak_tf, _, how = peaks()
+        gf = GFLOP_PER_SAMPLE_FWD if HW == 256 else None
+        tf = 3 * gf * B / ms if gf else None
+        print(json.dumps({
+            "metric": "images/sec (train_unet.py step: fwd + bwd + clip + AdamW + EMA, 256x256x1)", "mode": "train",
+            "value": B * world / ms * 1e3, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 activations and activation gradients, fp32 parameters / parameter gradients / optimizer",
+            "data": "synthetic (uint8 images -> [-1,1], random-init weights seed 0)",
+            "config": {"workload": f"train_unet.py iteration, batch={B} per GPU, {HW}x{HW}x1, {world}xB200",
+                       "global_batch": B * world, "parallelism": f"dp{world} (one all-reduce of the flat gradient buffer per step)"},
+            "clocks": clocks, "gpu_launches": (model.last_launch_count + model.last_backward_launch_count + 4) * args.steps,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": tf / peak_tf if tf else None, "peak_source": f"{how} bf16 sustained (MEASURED_PEAKS.json)",
+                         "traffic": None, "flops_model": "3 x 496.42 GFLOP per sample (SURVEY §8d)"},
+            "loss": float(loss)}))
+    if use_dist:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", default="sample", choices=["sample", "train"],
+                    help="sample = the headline metric (default); train = one train_unet.py iteration per step")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -317,8 +390,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--dump-ops", default=None, help="write the per-launch profile (kind, ms, flops) to this JSON")
     args = ap.parse_args()
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version banner to stdout)
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "train":
+        run_train(args)
     else:
         run_b200(args)
 

@@ -110,3 +110,22 @@ def test_vae_c4_resolution(cuda):
     z = m_ref[:, :1].contiguous()
     y = model.decode(z.to(cuda))["sample"]
     _cmp("decode", y.cpu(), decode(w, ocfg, z), **DEC_OUT)
+
+
+def test_vae_rgb_hub_shape(cuda):
+    """Hub VAEs are 3-channel RGB with 4 latent channels (scripts/train_unet.py:81-82, pipeline_audio_diffusion.py:198):
+    the generic conv_in (cin = 3 / 4), the 8-wide moments tail and the cout = 3 output kernel."""
+    from oracle.vae_oracle import decode, encode_moments, posterior_sample
+    model, ocfg, w = _build(cuda, seed=9, in_channels=3, out_channels=3, latent_channels=4)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 3, 32, 32, generator=g).clamp(-1, 1)
+    m_ref = encode_moments(w, ocfg, x)
+    post = model.encode(x.to(cuda)).latent_dist
+    z = post.sample(generator=torch.Generator().manual_seed(4))
+    noise = torch.randn(z.shape, generator=torch.Generator().manual_seed(4))
+    _cmp("moments", post.parameters.cpu(), m_ref)
+    _cmp("z", z.cpu(), posterior_sample(m_ref, noise), max_tol=6e-2, rms_tol=1.5e-2)
+    zr = m_ref[:, :4].contiguous()
+    y = model.decode(zr.to(cuda))["sample"]
+    assert y.shape == (2, 3, 32, 32)
+    _cmp("decode", y.cpu(), decode(w, ocfg, zr), **DEC_OUT)
