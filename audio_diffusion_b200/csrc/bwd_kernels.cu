@@ -29,10 +29,6 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 constexpr int GB_THREADS = 256;
 constexpr int GB_PIX = 4096;   // pixels per CTA in the reduction pass
 
-struct GnConst {   // per-channel constants of one 8-channel plane, built per thread from shared tables
-  float scale[8], shift[8];
-};
-
 __device__ __forceinline__ void group_stats(const GnBwdParams& p, int n, float* gmean, float* grstd) {
   const int Ct = p.C[0] + p.C[1];
   const int cpg = Ct / p.groups;
