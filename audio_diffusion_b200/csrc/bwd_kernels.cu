@@ -102,21 +102,8 @@ __global__ void __launch_bounds__(GB_THREADS) gn_bwd_reduce_kernel(const GnBwdPa
     for (int k = 0; k < GB_THREADS / 32; ++k) t += red[k][threadIdx.x];
     const int e = threadIdx.x & 7, which = threadIdx.x >> 3;
     atomicAdd(p.sums + ((long long)n * Ct + pl * 8 + e) * 2 + which, t);
+    if (p.dgamma) atomicAdd((which ? p.dgamma : p.dbeta) + pl * 8 + e, t);   // dbeta = sum S1, dgamma = sum S2 over n
   }
-}
-
-// dgamma / dbeta: one thread per channel sums over the samples
-__global__ void gn_bwd_param_kernel(const GnBwdParams p) {
-  const int Ct = p.C[0] + p.C[1];
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= Ct) return;
-  float a = 0.f, b = 0.f;
-  for (int n = 0; n < p.N; ++n) {
-    a += p.sums[((long long)n * Ct + c) * 2];
-    b += p.sums[((long long)n * Ct + c) * 2 + 1];
-  }
-  atomicAdd(p.dbeta + c, a);
-  atomicAdd(p.dgamma + c, b);
 }
 
 // pass 2: grid (pixel chunks of 256, planes, N): gx (+ optional addends) for one pixel x one plane per thread
@@ -182,10 +169,6 @@ cudaError_t launch_gn_bwd(const GnBwdParams& p, cudaStream_t s) {
   const int hw = p.H * p.W;
   gn_bwd_reduce_kernel<<<dim3((hw + GB_PIX - 1) / GB_PIX, Ct >> 3, p.N), GB_THREADS, 0, s>>>(p);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  if (p.dgamma) {
-    gn_bwd_param_kernel<<<(Ct + 127) / 128, 128, 0, s>>>(p);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  }
   gn_bwd_apply_kernel<<<dim3((hw + GB_THREADS - 1) / GB_THREADS, Ct >> 3, p.N), GB_THREADS, 0, s>>>(p);
   return cudaGetLastError();
 }
@@ -193,7 +176,8 @@ cudaError_t launch_gn_bwd(const GnBwdParams& p, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------------------------------
 // out[n][c] = sum over pixels of src[n][c][.] (PF8 bf16 -> fp32).  `out` must be zeroed by the caller (launcher does).
 __global__ void __launch_bounds__(GB_THREADS) chan_sum_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ out,
-                                                              int N, int C, int img_planes, int H, int W) {
+                                                              int N, int C, int img_planes, int H, int W,
+                                                              float* __restrict__ bias0, float* __restrict__ bias1) {
   __shared__ float red[GB_THREADS / 32][8];
   const int n = blockIdx.z, pl = blockIdx.y;
   const Geom g = make_geom(N, H, W);
@@ -219,12 +203,16 @@ __global__ void __launch_bounds__(GB_THREADS) chan_sum_kernel(const __nv_bfloat1
     float t = 0.f;
     for (int k = 0; k < GB_THREADS / 32; ++k) t += red[k][threadIdx.x];
     atomicAdd(out + (long long)n * C + pl * 8 + threadIdx.x, t);
+    if (bias0) atomicAdd(bias0 + pl * 8 + threadIdx.x, t);     // bias gradient = sum over samples and pixels
+    if (bias1) atomicAdd(bias1 + pl * 8 + threadIdx.x, t);
   }
 }
-cudaError_t launch_chan_sum(const __nv_bfloat16* src, float* out, int N, int C, int img_planes, int H, int W, cudaStream_t s) {
+cudaError_t launch_chan_sum(const __nv_bfloat16* src, float* out, int N, int C, int img_planes, int H, int W, cudaStream_t s,
+                            float* bias0, float* bias1) {
   cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * C * sizeof(float), s);
   if (e != cudaSuccess) return e;
-  chan_sum_kernel<<<dim3((H * W + GB_PIX - 1) / GB_PIX, C >> 3, N), GB_THREADS, 0, s>>>(src, out, N, C, img_planes, H, W);
+  chan_sum_kernel<<<dim3((H * W + GB_PIX - 1) / GB_PIX, C >> 3, N), GB_THREADS, 0, s>>>(src, out, N, C, img_planes, H, W,
+                                                                                          bias0, bias1);
   return cudaGetLastError();
 }
 

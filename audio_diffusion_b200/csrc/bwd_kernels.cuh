@@ -24,7 +24,9 @@ struct GnBwdParams {
 cudaError_t launch_gn_bwd(const GnBwdParams& p, cudaStream_t s);
 
 // out[n][c] = sum_pix src[n][c] for a C-channel view of a tensor with img_planes planes per image
-cudaError_t launch_chan_sum(const __nv_bfloat16* src, float* out, int N, int C, int img_planes, int H, int W, cudaStream_t s);
+// bias0 / bias1 (optional): the sample-summed channel sums are also added there (bias gradients)
+cudaError_t launch_chan_sum(const __nv_bfloat16* src, float* out, int N, int C, int img_planes, int H, int W, cudaStream_t s,
+                            float* bias0 = nullptr, float* bias1 = nullptr);
 cudaError_t launch_reduce_n_add(const float* src, float* dst, float* dst2, int N, int C, cudaStream_t s);
 cudaError_t launch_scatter_rows(const float* src, float* dst, int N, int C, int dstride, int doff, cudaStream_t s);
 cudaError_t launch_pf8_add(__nv_bfloat16* dst, const __nv_bfloat16* src, int N, int C, int H, int W, cudaStream_t s);

@@ -3,15 +3,16 @@
 // the DDPM/DDIM update, nearest-2x upsample, stride-2 parity split and layout conversion.
 // Reference semantics: diffusers UNet2DModel / DDPMScheduler.step / DDIMScheduler.step as called from
 // audiodiffusion/pipeline_audio_diffusion.py:163-179 (restated in oracle/unet_oracle.py, oracle/schedulers_oracle.py).
+#include <cstring>
+
 #include "kernels.cuh"
 
 namespace b200ad {
 
 // ------------------------------------------------------------------------------------ weight packing
-__global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin_total, int KH, int KW, int cin_off,
-                                    int ksteps, PackTaps taps, __nv_bfloat16* __restrict__ dst, long long nvec, int cout_real) {
-  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= nvec) return;
+__device__ __forceinline__ void pack_one_vector(const float* __restrict__ w, int cout, int cin_total, int KH, int KW,
+                                                int cin_off, int ksteps, const PackTaps& taps,
+                                                __nv_bfloat16* __restrict__ dst, long long id, int cout_real) {
   const int r = (int)(id & 7);
   const int n8 = (int)((id >> 3) & 15);
   const int k8 = (int)((id >> 7) & 1);
@@ -43,6 +44,55 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int c
   o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
   o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
   reinterpret_cast<uint4*>(dst)[id] = o;
+}
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin_total, int KH, int KW, int cin_off,
+                                    int ksteps, PackTaps taps, __nv_bfloat16* __restrict__ dst, long long nvec, int cout_real) {
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= nvec) return;
+  pack_one_vector(w, cout, cin_total, KH, KW, cin_off, ksteps, taps, dst, id, cout_real);
+}
+
+// one launch for a whole job table: block b packs vectors [256 * first, 256 * first + 256) of job blk[b].x
+__global__ void __launch_bounds__(256) pack_batch_kernel(const PackItem* __restrict__ items, const int2* __restrict__ blk) {
+  __shared__ PackItem it;
+  const int2 bj = blk[blockIdx.x];
+  if (threadIdx.x == 0) it = items[bj.x];
+  __syncthreads();
+  const long long id = (long long)bj.y * 256 + threadIdx.x;
+  if (id >= it.nvec) return;
+  pack_one_vector(it.w, it.cout, it.cin_total, it.KH, it.KW, it.cin_off, it.ksteps, it.taps, it.dst, id, it.cout_real);
+}
+
+PackBatch::~PackBatch() {
+  if (d_items) cudaFree(d_items);
+  if (d_blk) cudaFree(d_blk);
+}
+
+cudaError_t launch_pack_batch(PackBatch& pb, const std::vector<PackItem>& items, cudaStream_t s) {
+  if (items.empty()) return cudaSuccess;
+  const bool same = pb.host.size() == items.size() &&
+                    memcmp(pb.host.data(), items.data(), items.size() * sizeof(PackItem)) == 0;
+  if (!same) {
+    std::vector<int2> blk;
+    for (size_t j = 0; j < items.size(); ++j) {
+      const int nb = (int)((items[j].nvec + 255) / 256);
+      for (int b = 0; b < nb; ++b) blk.push_back(make_int2((int)j, b));
+    }
+    cudaError_t e = cudaStreamSynchronize(s);          // the old tables may still be in use
+    if (e != cudaSuccess) return e;
+    if (pb.d_items) cudaFree(pb.d_items);
+    if (pb.d_blk) cudaFree(pb.d_blk);
+    pb.d_items = pb.d_blk = nullptr;
+    if ((e = cudaMalloc(&pb.d_items, items.size() * sizeof(PackItem))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&pb.d_blk, blk.size() * sizeof(int2))) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(pb.d_items, items.data(), items.size() * sizeof(PackItem), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(pb.d_blk, blk.data(), blk.size() * sizeof(int2), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    pb.host = items;
+    pb.nblocks = (int)blk.size();
+  }
+  pack_batch_kernel<<<pb.nblocks, 256, 0, s>>>((const PackItem*)pb.d_items, (const int2*)pb.d_blk);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_pack_weights(const float* w, int cout, int cin_total, int KH, int KW, int cin_off, int ksteps,

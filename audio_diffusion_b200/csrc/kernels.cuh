@@ -1,5 +1,6 @@
 // Launchers of the non-tensor-core kernels of the U-Net path (elementwise.cu, attention.cu, temb.cu).
 #pragma once
+#include <vector>
 #include "common.cuh"
 
 namespace b200ad {
@@ -19,6 +20,27 @@ struct PackTaps {
 };
 cudaError_t launch_pack_weights(const float* w, int cout, int cin_total, int KH, int KW, int cin_off, int ksteps,
                                 const PackTaps& taps, __nv_bfloat16* dst, cudaStream_t s, int cout_real = -1);
+
+// Batched form: all K-segments of a model in ONE launch. `PackBatch` owns a small device-side job table, rebuilt only when
+// a source / destination pointer changes.
+struct PackItem {
+  const float* w;
+  __nv_bfloat16* dst;
+  int cout, cin_total, KH, KW, cin_off, ksteps, cout_real;
+  PackTaps taps;
+  long long nvec;
+};
+struct PackBatch {
+  std::vector<PackItem> host;      // last uploaded table
+  void* d_items = nullptr;         // PackItem[njobs]
+  void* d_blk = nullptr;           // int2 {job, first vector of the block / 256} per block
+  int nblocks = 0;
+  PackBatch() = default;
+  PackBatch(const PackBatch&) = delete;
+  PackBatch& operator=(const PackBatch&) = delete;
+  ~PackBatch();
+};
+cudaError_t launch_pack_batch(PackBatch& pb, const std::vector<PackItem>& items, cudaStream_t s);
 
 // nearest-2x upsample + 3x3 conv, output parity (a, b): a 2x2 conv on the low-res input whose taps are sums of the 3x3
 // taps that read the same low-res pixel. Row taps: a = 0 -> dh = -1 (kh 0), dh = 0 (kh 1,2); a = 1 -> dh = 0 (kh 0,1), +1 (kh 2).

@@ -103,7 +103,20 @@ struct NetBase {
   float* temb_u2 = nullptr;         // [N][4 dim0]    linear_2 output before SiLU
   int num_sms = 148;
   int last_launches = 0;
+  PackBatch pack_batch;             // device job table of the weight packing (one launch for all K-segments)
 };
+
+static PackItem make_pack_item(const NetBase* h, const PackJob& j, uint8_t* arena) {
+  PackItem it;
+  memset(&it, 0, sizeof(it));       // padding included: the table is compared bytewise
+  it.w = h->pptr[j.w_param];
+  it.dst = (__nv_bfloat16*)(arena + j.off);
+  it.cout = j.cout; it.cin_total = j.cin_total; it.KH = j.KH; it.KW = j.KW; it.cin_off = j.cin_off; it.ksteps = j.ksteps;
+  it.cout_real = j.cout_real < 0 ? j.cout : j.cout_real;
+  it.taps = j.taps;
+  it.nvec = (long long)(j.cout / 128) * j.ksteps * j.taps.ntaps * 256;
+  return it;
+}
 
 static void add_param(NetBase* h, const std::string& name, std::vector<int64_t> shape) {
   h->pidx[name] = (int)h->params.size();
@@ -233,9 +246,12 @@ static bool ends_with(const std::string& s, const char* suf) {
 
 // Pack every conv K-segment, the identity blocks and the fused bias vectors into the arena (after pptr/packed are set).
 static int pack_common(NetBase* h, cudaStream_t st) {
-  for (const PackJob& j : h->jobs)
-    CK(launch_pack_weights(h->pptr[j.w_param], j.cout, j.cin_total, j.KH, j.KW, j.cin_off, j.ksteps, j.taps,
-                           (__nv_bfloat16*)(h->packed + j.off), st, j.cout_real));
+  {
+    std::vector<PackItem> items;
+    items.reserve(h->jobs.size());
+    for (const PackJob& j : h->jobs) items.push_back(make_pack_item(h, j, h->packed));
+    CK(launch_pack_batch(h->pack_batch, items, st));
+  }
   for (const auto& kv : h->ident_off) CK(launch_pack_identity(kv.first, (__nv_bfloat16*)(h->packed + kv.second), st));
   for (const auto& kv : h->misc_off) {
     const std::string& key = kv.first;

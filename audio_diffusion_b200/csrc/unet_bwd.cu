@@ -50,6 +50,7 @@ struct Backward {
   size_t arena_bytes = 0;
   float* grads = nullptr;
   int launches = 0;
+  PackBatch pack_batch;              // one launch for all transposed packs
 };
 
 namespace b200ad {
@@ -183,11 +184,9 @@ struct BwdBuilder {
     BOp op{};
     op.kind = BOp::CHANSUM;
     op.src = g.p; op.o0 = cs; op.C = g.C; op.a = g.img_planes; op.H = g.H; op.W = g.W;
+    op.o1 = PG(bname);                                        // bias gradient(s) accumulated by the same kernel
+    op.f1 = bname2.empty() ? nullptr : PG(bname2);
     bw->ops.push_back(op);
-    BOp r{};
-    r.kind = BOp::REDUCE_N;
-    r.f0 = cs; r.o0 = PG(bname); r.o1 = bname2.empty() ? nullptr : PG(bname2); r.C = g.C;
-    bw->ops.push_back(r);
   }
   Act gn_apply(const std::string& tag, const Act& a, const Act* b, const std::string& norm, bool silu) {
     const int Ct = a.C + (b ? b->C : 0);
@@ -672,19 +671,24 @@ extern "C" int b200ad_unet_backward(b200ad_unet* h, const float* x, const float*
     CK(cudaEventRecord(ev[0], st));
   }
   CK(cudaMemsetAsync(bw->grads, 0, bw->grad_floats * sizeof(float), st));
-  for (const PackJob& j : bw->jobs)
-    CK(launch_pack_weights(h->pptr[j.w_param], j.cout, j.cin_total, j.KH, j.KW, j.cin_off, j.ksteps, j.taps,
-                           (__nv_bfloat16*)(bw->arena + j.off), st, j.cout_real));
-  launches += (int)bw->jobs.size();
+  {
+    std::vector<PackItem> items;
+    items.reserve(bw->jobs.size());
+    for (const PackJob& j : bw->jobs) items.push_back(make_pack_item(h, j, bw->arena));
+    CK(launch_pack_batch(bw->pack_batch, items, st));
+  }
+  launches += 1;
   if (prof) CK(cudaEventRecord(ev[1], st));
   size_t opi = 0;
   for (BOp& op : bw->ops) {
     switch (op.kind) {
       case BOp::CONV: CK(launch_conv_tc(op.conv, h->num_sms, st)); break;
       case BOp::WGRAD: CK(launch_wgrad_tc(op.wg, h->num_sms, st)); break;
-      case BOp::GNBWD: CK(launch_gn_bwd(op.gb, st)); launches += 2; break;
+      case BOp::GNBWD: CK(launch_gn_bwd(op.gb, st)); launches += 1; break;
       case BOp::GNAPPLY: CK(launch_gn_apply(op.ga, st)); break;
-      case BOp::CHANSUM: CK(launch_chan_sum(op.src, op.o0, N, op.C, op.a, op.H, op.W, st)); break;
+      case BOp::CHANSUM:
+        CK(launch_chan_sum(op.src, op.o0, N, op.C, op.a, op.H, op.W, st, op.o1, const_cast<float*>(op.f1)));
+        break;
       case BOp::REDUCE_N: CK(launch_reduce_n_add(op.f0, op.o0, op.o1, N, op.C, st)); break;
       case BOp::SCATTER: CK(launch_scatter_rows(op.f0, op.o0, N, op.C, op.a, op.b, st)); break;
       case BOp::PF8ADD: CK(launch_pf8_add(op.dst, op.src, N, op.C, op.H, op.W, st)); break;
