@@ -15,9 +15,10 @@ def broadcast_parameters(params: Iterable[torch.Tensor], src: int = 0) -> None:
     flat = torch.cat([p.data.reshape(-1) for p in params])
     dist.broadcast(flat, src=src)
     off = 0
-    for p in params:
-        p.data.copy_(flat[off:off + p.numel()].view_as(p))
-        off += p.numel()
+    with torch.no_grad():
+        for p in params:
+            p.copy_(flat[off:off + p.numel()].view_as(p))   # in place on the parameter: its version changes -> weights re-packed
+            off += p.numel()
 
 
 def shard_rows(n: int, rank: int, world: int) -> slice:

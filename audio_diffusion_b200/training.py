@@ -80,7 +80,7 @@ class EMAModel:
     @torch.no_grad()
     def copy_to(self, parameters: Iterable[torch.nn.Parameter]) -> None:
         for s, p in zip(self.shadow_params, parameters):
-            p.data.copy_(s.to(p.device))
+            p.copy_(s.to(p.device))     # in-place on the parameter itself: bumps its version (the U-Net re-packs its weights)
 
     def to(self, device=None, dtype=None):
         self.shadow_params = [s.to(device=device, dtype=dtype) if s.is_floating_point() else s.to(device=device)

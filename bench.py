@@ -155,13 +155,8 @@ def run_b200(args):
     model = UNet2DModel(sample_size=(HW, HW), seed=0, **REF_ARCH).to(dev)
     if use_dist:
         # batched sampling shards over GPUs: ONE broadcast of the weights at init, no per-step collective
-        flat = torch.cat([p.data.reshape(-1) for p in model.parameters()])
-        dist.broadcast(flat, src=0)
-        off = 0
-        for p in model.parameters():
-            p.data.copy_(flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
-        del flat
+        from audio_diffusion_b200.parallel import broadcast_parameters
+        broadcast_parameters(model.parameters(), src=0)
     sch = DDPMScheduler()
     sch.set_timesteps(DDPM_STEPS)
     g = torch.Generator(device=dev).manual_seed(42 + rank)

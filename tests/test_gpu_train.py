@@ -207,3 +207,20 @@ def test_unet_backward_reference_architecture(cuda):
     gmax = max(r[2] for r in rows)
     bad = [(e, k) for e, k, s, _ in rows if e > 0.10 and s > 1e-3 * gmax]
     assert total <= 3e-2 and not bad, (total, bad[:10])
+
+
+def test_ema_copy_to_refreshes_packed_weights(cuda):
+    """scripts/train_unet.py:292-301: `ema_model.copy_to(unet.parameters())` right before sampling — the engine must notice
+    that the parameters changed (its bf16-packed copy is keyed on parameter versions)."""
+    from audio_diffusion_b200.training import EMAModel
+    from audio_diffusion_b200.unet import UNet2DModel
+    m = UNet2DModel(sample_size=(32, 32), seed=1, **TRAIN_CFG).to(cuda)
+    x = torch.randn(1, 1, 32, 32, generator=torch.Generator().manual_seed(0)).to(cuda)
+    with torch.no_grad():
+        a = m(x, 10)["sample"].clone()
+        ema = EMAModel(m.parameters())
+        for s in ema.shadow_params:
+            s.mul_(0.5)
+        ema.copy_to(m.parameters())
+        b = m(x, 10)["sample"].clone()
+    assert (a - b).abs().max() > 1e-3 * a.abs().max()
