@@ -140,7 +140,11 @@ extern "C" int b200ad_unet_create(const b200ad_unet_config* cfg, b200ad_unet** o
   *out = h;
   return 0;
 }
-extern "C" void b200ad_unet_destroy(b200ad_unet* h) { delete h; }
+extern "C" void b200ad_unet_destroy(b200ad_unet* h) {
+  if (!h) return;
+  release_backward(h);
+  delete h;
+}
 extern "C" int b200ad_unet_num_params(const b200ad_unet* h) { return (int)h->params.size(); }
 extern "C" const char* b200ad_unet_param_name(const b200ad_unet* h, int i) { return h->params[i].name.c_str(); }
 extern "C" int b200ad_unet_param_shape(const b200ad_unet* h, int i, int64_t* dims) {

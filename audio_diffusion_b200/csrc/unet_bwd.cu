@@ -604,6 +604,13 @@ static int build_backward(b200ad_unet* h, Backward* bw, uint8_t* arena, float* g
 
 }  // namespace b200ad
 
+namespace b200ad {
+void release_backward(b200ad_unet* h) {
+  delete h->bwd;
+  h->bwd = nullptr;
+}
+}  // namespace b200ad
+
 // ================================================================================= C ABI
 extern "C" int b200ad_unet_set_training(b200ad_unet* h, int on) {
   if (!h) return set_err("null handle");
