@@ -58,10 +58,6 @@ struct WgradDesc {
   int cin_total, ci_off, ntaps_total;
   int ntaps;
   int dh[9], dw_[9], tapidx[9];
-  // optional: `act` is the RAW forward tensor and the GroupNorm(+SiLU) is re-applied while staging (as the forward conv does)
-  const float2* ss;        // [N][ss_stride] (scale, shift) of gn_finalize, or null
-  int ss_stride, ss_off;   // channels of the whole norm, first channel of this view inside it
-  int silu;
 };
 cudaError_t launch_wgrad_tc(const WgradDesc& d, int num_sms, cudaStream_t s);
 

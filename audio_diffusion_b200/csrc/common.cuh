@@ -219,27 +219,6 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
-// (shared by the forward conv's and the weight-gradient kernel's transform warps)
-// one 16-byte vector (8 channels of one pixel): affine + optional SiLU in fp32, back to bf16.
-// With SiLU the caller passes HALVED scale/shift: h = a/2 = x*s' + t', silu(a) = a * (0.5 + 0.5 tanh(a/2)) = h + h * tanh(h)
-// -> FFMA, MUFU.TANH, FFMA per element.
-template <bool SILU>
-__device__ __forceinline__ uint4 xform_vec(uint4 v, const float2 (&ss)[8]) {
-  uint32_t u[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float2 f = unpack_bf16x2(u[e]);
-    float a = fmaf(f.x, ss[2 * e].x, ss[2 * e].y);
-    float b = fmaf(f.y, ss[2 * e + 1].x, ss[2 * e + 1].y);
-    if (SILU) {
-      a = fmaf(a, tanh_approx(a), a);
-      b = fmaf(b, tanh_approx(b), b);
-    }
-    u[e] = pack_bf16x2(a, b);
-  }
-  return make_uint4(u[0], u[1], u[2], u[3]);
-}
-
 #endif  // __CUDACC__
 
 }  // namespace b200ad

@@ -49,6 +49,26 @@ __device__ __forceinline__ WorkItem decode_work(const ConvParams& p, int w) {
   return wi;
 }
 
+// one 16-byte vector (8 channels of one pixel): affine + optional SiLU in fp32, back to bf16.
+// With SiLU the caller passes HALVED scale/shift: h = a/2 = x*s' + t', silu(a) = a * (0.5 + 0.5 tanh(a/2)) = h + h * tanh(h)
+// -> FFMA, MUFU.TANH, FFMA per element.
+template <bool SILU>
+__device__ __forceinline__ uint4 xform_vec(uint4 v, const float2 (&ss)[8]) {
+  uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = unpack_bf16x2(u[e]);
+    float a = fmaf(f.x, ss[2 * e].x, ss[2 * e].y);
+    float b = fmaf(f.y, ss[2 * e + 1].x, ss[2 * e + 1].y);
+    if (SILU) {
+      a = fmaf(a, tanh_approx(a), a);
+      b = fmaf(b, tanh_approx(b), b);
+    }
+    u[e] = pack_bf16x2(a, b);
+  }
+  return make_uint4(u[0], u[1], u[2], u[3]);
+}
+
 template <int MAXG, int ACC, int AS, int BS>
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];

@@ -93,7 +93,6 @@ struct NetBase {
   size_t ws_bytes = 0;
   std::vector<Op> plan;
   std::map<std::string, Act> taps;
-  std::map<std::string, float2*> ss_taps;   // GroupNorm name -> per-(sample, channel) scale/shift written by gn_finalize
   stat_t* stats_arena = nullptr;
   size_t stats_bytes = 0;
   float* temb_act = nullptr;
@@ -367,7 +366,6 @@ struct Builder {
     p.N = N; p.H = a.H; p.W = a.W; p.groups = h->norm_groups; p.eps = h->norm_eps; p.silu = 0;
     op.ss = ss;
     plan->push_back(op);
-    h->ss_taps[norm] = ss;
     return ss;
   }
   static void seg_norm(ConvSeg& s, const float2* ss, int stride, bool silu) {

@@ -5,8 +5,7 @@
 //     as four scatter launches, the folded upsampling convs as one gather launch over the parity planes of the gradient);
 //   * weight gradients run on wgrad_tc_kernel (tcgen05, pixels as the reduction dimension, MN-major operands);
 //   * GroupNorm(+SiLU), attention core, biases / time embedding, conv_in / conv_out are memory-bound kernels (bwd_kernels.cu).
-// The weight-gradient kernel re-applies GroupNorm(+SiLU) to the raw activations while staging them (as the forward conv
-// does); GroupNorm backward itself is still two separate memory-bound passes — DESIGN.md §3 "Training step".
+// This first version materialises the normalised activations for the weight gradients (no fusion yet) — DESIGN.md §6.
 #include "bwd_kernels.cuh"
 #include "unet.cuh"
 
@@ -163,17 +162,11 @@ struct BwdBuilder {
     op.conv.nseg = 1;
     bw->ops.push_back(op);
   }
-  // norm != "": `act` is the RAW forward tensor; its GroupNorm (scale/shift of gn_finalize, channel offset ss_off inside the
-  // norm's concatenated channel space) and optional SiLU are re-applied inside the weight-gradient kernel's staging.
   void wgrad(const View& gy, const View& act, float* dw, int cin_total, int ci_off, int ntaps_total, int ntaps,
-             const signed char* dh, const signed char* dwv, const int* tapidx, const std::string& norm = "",
-             int ss_stride = 0, int ss_off = 0, bool silu = false) {
+             const signed char* dh, const signed char* dwv, const int* tapidx) {
     BOp op{};
     op.kind = BOp::WGRAD;
     WgradDesc& d = op.wg;
-    if (!norm.empty()) {
-      d.ss = h->ss_taps.at(norm); d.ss_stride = ss_stride; d.ss_off = ss_off; d.silu = silu ? 1 : 0;
-    }
     d.gy = gy.p; d.act = act.p; d.dw = dw; d.N = N; d.H = gy.H; d.W = gy.W; d.cout = gy.C; d.cin = act.C;
     d.gy_img_planes = gy.img_planes; d.act_img_planes = act.img_planes;
     d.cin_total = cin_total; d.ci_off = ci_off; d.ntaps_total = ntaps_total; d.ntaps = ntaps;
@@ -185,16 +178,6 @@ struct BwdBuilder {
     int ti[9];
     for (int k = 0; k < K * K; ++k) { dh[k] = (signed char)(k / K - K / 2); dw[k] = (signed char)(k % K - K / 2); ti[k] = k; }
     wgrad(gy, act, PG(wname), act.C, 0, K * K, K * K, dh, dw, ti);
-  }
-  // stride-1 conv whose input is norm(+SiLU) of cat(a, b): one launch per raw source, normalisation fused into the kernel
-  void wgrad_conv_normed(const View& gy, const Act& a, const Act* b, const std::string& wname, int K,
-                         const std::string& norm, bool silu) {
-    signed char dh[9], dw[9];
-    int ti[9];
-    for (int k = 0; k < K * K; ++k) { dh[k] = (signed char)(k / K - K / 2); dw[k] = (signed char)(k % K - K / 2); ti[k] = k; }
-    const int Ct = a.C + (b ? b->C : 0);
-    wgrad(gy, whole(a), PG(wname), Ct, 0, K * K, K * K, dh, dw, ti, norm, Ct, 0, silu);
-    if (b) wgrad(gy, whole(*b), PG(wname), Ct, a.C, K * K, K * K, dh, dw, ti, norm, Ct, a.C, silu);
   }
   // per-channel sums of a gradient -> bias gradient(s); returns the [N][C] scratch (valid until the next chan_sum)
   void bias_grad(const View& g, const std::string& bname, const std::string& bname2 = "") {
@@ -252,7 +235,8 @@ struct BwdBuilder {
     // conv2
     Act T1 = tmp("T1", co, H, W);
     dgrad(n + ".conv2.T", n + ".conv2.weight", whole(Gout), T1, 3);
-    wgrad_conv_normed(whole(Gout), h1, nullptr, n + ".conv2.weight", 3, n + ".norm2", true);
+    Act A = gn_apply("A", h1, nullptr, n + ".norm2", true);
+    wgrad_conv(whole(Gout), whole(A), n + ".conv2.weight", 3);
     const bool sc = Ct != co;
     bias_grad(whole(Gout), n + ".conv2.bias", sc ? n + ".conv_shortcut.bias" : "");
     // norm2 + SiLU
@@ -269,7 +253,8 @@ struct BwdBuilder {
     // conv1
     Act T2 = tmp("T2", Ct, H, W);
     dgrad(n + ".conv1.T", n + ".conv1.weight", whole(Gh1), T2, 3);
-    wgrad_conv_normed(whole(Gh1), a, has_b ? &bsrc : nullptr, n + ".conv1.weight", 3, n + ".norm1", true);
+    Act A2 = gn_apply("A2", a, has_b ? &bsrc : nullptr, n + ".norm1", true);
+    wgrad_conv(whole(Gh1), whole(A2), n + ".conv1.weight", 3);
     // shortcut
     const __nv_bfloat16* addS;
     if (sc) {
@@ -308,10 +293,11 @@ struct BwdBuilder {
       op.src = qkv.p; op.src2 = T1.p; op.dst = Gqkv.p; op.C = C; op.H = H; op.W = W;
       bw->ops.push_back(op);
     }
+    Act XN = gn_apply("A", x, nullptr, n + ".group_norm", false);
     const char* names[3] = {"to_q", "to_k", "to_v"};
     for (int k = 0; k < 3; ++k) {
       const View gv = view(Gqkv, k * C, C);
-      wgrad_conv_normed(gv, x, nullptr, n + "." + names[k] + ".weight", 1, n + ".group_norm", false);
+      wgrad_conv(gv, whole(XN), n + "." + names[k] + ".weight", 1);
       bias_grad(gv, n + "." + names[k] + ".bias");
     }
     // g(norm(x)) = sum over q, k, v of W^T g: one launch, three K-segments

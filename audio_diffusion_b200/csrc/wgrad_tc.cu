@@ -29,8 +29,6 @@ struct WgradParams {
   int row_tapidx[3][3];       // destination tap index
   int P;                      // pixels per staged block (multiple of 16)
   int nblk;                   // blocks per image
-  const float2* ss;           // fused GroupNorm(+SiLU) of the activation operand (null: `act` is used as stored)
-  int ss_stride, ss_off, silu;
 };
 
 constexpr int WG_THREADS = 192;   // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
@@ -44,17 +42,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   const int act_bytes = (NCI / 8) * act_pix * 16;
   const int stage_bytes = (gy_bytes + act_bytes + 127) & ~127;
   uint8_t* ctrl = smem + STAGES * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);         // full[S], empty[S], ready[S], done
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);         // full[S], empty[S], done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + 128);
-  float2* sst = reinterpret_cast<float2*>(ctrl + 256);        // [NCI] scale/shift of the current block's sample
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES), bar_ready = smem_u32(bars + 2 * STAGES),
-                 bar_done = smem_u32(bars + 3 * STAGES);
-  const bool fused = p.ss != nullptr;
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES), bar_done = smem_u32(bars + 2 * STAGES);
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); mbar_init(bar_ready + 8 * s, 128);
-    }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_done, 1);
     mbar_fence_init();
   }
@@ -100,7 +93,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     uint32_t phase = 0;
     uint32_t first = 1;
     for (int b = blockIdx.x; b < total_blocks; b += gridDim.x) {
-      mbar_wait_warp((fused ? bar_ready : bar_full) + 8 * stage, phase);   // fused: the window has been normalised in place
+      mbar_wait_warp(bar_full + 8 * stage, phase);
       tc_fence_after();
       const uint32_t a16 = (smem_base + stage * stage_bytes) >> 4;
       const uint32_t b16 = a16 + ((uint32_t)gy_bytes >> 4);
@@ -133,49 +126,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     }
     umma_commit_elect(bar_done);
   } else {
-    // warps 2-5. While the pixel blocks stream: (fused mode) GroupNorm(+SiLU) of the landed activation window in place —
-    // x * scale[n][c] + shift[n][c], SiLU, zero outside the image — exactly what the forward conv's transform warps do.
-    const int q = warp & 3;
-    if (fused) {
-      const int tt = (warp - 2) * 32 + lane;            // 0..127
-      const int roff = p.row_off[row];
-      const int hw_end = p.H * p.Wp;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int b = blockIdx.x; b < total_blocks; b += gridDim.x) {
-        const int n = b / p.nblk, m0 = (b - n * p.nblk) * p.P;
-        // this sample's scale / shift for the CTA's channels (halved for the tanh form of SiLU, see xform_vec)
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // previous block's readers are done with the table
-        if (tt < NCI) {
-          float2 v = __ldg(p.ss + (long long)n * p.ss_stride + p.ss_off + cj * NCI + tt);
-          if (p.silu) { v.x *= 0.5f; v.y *= 0.5f; }
-          sst[tt] = v;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        mbar_wait(bar_full + 8 * stage, phase);
-        uint4* win = reinterpret_cast<uint4*>(smem + stage * stage_bytes + gy_bytes);
-        for (int i = tt; i < act_pix; i += 128) {
-          const int m = m0 + roff - 1 + i;
-          const bool valid = m >= 0 && m < hw_end && (m % p.Wp) < p.W;
-#pragma unroll 2
-          for (int pl = 0; pl < NCI / 8; ++pl) {
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (valid) {
-              float2 sv[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) sv[e] = sst[pl * 8 + e];
-              v = win[pl * act_pix + i];
-              v = p.silu ? xform_vec<true>(v, sv) : xform_vec<false>(v, sv);
-            }
-            win[pl * act_pix + i] = v;
-          }
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(bar_ready + 8 * stage);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
     // epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 = output channels; columns = the CTA's input channels per tap
+    const int q = warp & 3;
     if (blockIdx.x < total_blocks) {
       mbar_wait(bar_done, 0);
       tc_fence_after();
@@ -202,7 +154,7 @@ template <int NCI, int STAGES>
 static cudaError_t launch_wg(const WgradParams& p, int num_sms, cudaStream_t s) {
   const int act_pix = p.P + 2;
   const int stage_bytes = (p.P * 256 + (NCI / 8) * act_pix * 16 + 127) & ~127;
-  const size_t smem = (size_t)STAGES * stage_bytes + 256 + NCI * sizeof(float2);
+  const size_t smem = (size_t)STAGES * stage_bytes + 256;
   if (smem > (size_t)CONV_SMEM_MAX) return cudaErrorInvalidValue;
   auto kern = wgrad_tc_kernel<NCI, STAGES>;
   static size_t attr = 0;
@@ -228,7 +180,6 @@ cudaError_t launch_wgrad_tc(const WgradDesc& d, int num_sms, cudaStream_t s) {
   p.N = d.N; p.H = d.H; p.W = d.W; p.Wp = g.Wp; p.lead = g.lead; p.PL = g.PL; p.cin = d.cin; p.cout = d.cout;
   p.gy_img_planes = d.gy_img_planes; p.act_img_planes = d.act_img_planes;
   p.cin_total = d.cin_total; p.ci_off = d.ci_off; p.ntaps_total = d.ntaps_total;
-  p.ss = d.ss; p.ss_stride = d.ss_stride; p.ss_off = d.ss_off; p.silu = d.silu;
   // group the taps into rows of equal dh
   p.nrows = 0;
   for (int t = 0; t < d.ntaps; ++t) {
