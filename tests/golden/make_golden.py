@@ -1,5 +1,5 @@
 """Generates tests/golden/* by running the reference's OWN Python files (read from /root/reference, unchanged) in this
-container.  Run from the repo root:  python tools/make_golden.py
+container.  Run from the repo root:  python tests/golden/make_golden.py
 
  * vae_key_map.json — output of audiodiffusion/utils.py::convert_ldm_vae_checkpoint on an ldm-format checkpoint of the
    config/ldm_autoencoder_kl.yaml shape: [hf key, shape] in the order the reference writes them.  Pins the parameter
@@ -15,7 +15,7 @@ import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 REF = "/root/reference"
 sys.path[:0] = [ROOT, os.path.join(ROOT, "audio_diffusion_b200", "compat"), REF, os.path.join(ROOT, "tests")]
 

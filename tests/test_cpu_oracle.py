@@ -366,7 +366,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
 def test_golden_vae_key_map_matches_library_table():
-    """tests/golden/vae_key_map.json (written by the reference's own converter, tools/make_golden.py) == libb200ad's
+    """tests/golden/vae_key_map.json (written by the reference's own converter, tests/golden/make_golden.py) == libb200ad's
     AutoencoderKL parameter table after diffusers' deprecated-attention renames (names AND shapes)."""
     import ctypes as C
     import json
@@ -397,7 +397,7 @@ def test_golden_vae_key_map_matches_library_table():
 
 def test_golden_pipeline_images_match_oracle_loop():
     """tests/golden/pipeline_ddpm_small.npz was produced by the reference's unchanged AudioDiffusionPipeline.__call__
-    (tools/make_golden.py); the oracle's own loop (oracle U-Net + OracleDDPM, same noise draws) gives the same bytes."""
+    (tests/golden/make_golden.py); the oracle's own loop (oracle U-Net + OracleDDPM, same noise draws) gives the same bytes."""
     from oracle.schedulers_oracle import OracleDDPM
     from oracle.unet_oracle import UNetConfig, init_weights, unet_forward
     z = np.load(os.path.join(GOLDEN, "pipeline_ddpm_small.npz"))
