@@ -412,3 +412,38 @@ def test_golden_pipeline_images_match_oracle_loop():
         x = sch.step(unet_forward(w, cfg, x, t), t, x, generator=gen)["prev_sample"]
     img = ((x / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1).numpy() * 255).round().astype("uint8")[:, :, :, 0]
     assert np.array_equal(img, z["images"])
+
+
+def test_training_host_logic_without_gpu():
+    """EMAModel's schedule and CPU shadow update (diffusers 0.24 surface: step / copy_to / get_decay, deprecated max_value /
+    inv_gamma / power kwargs as scripts/train_unet.py:185-190 passes them), and the product's refusal to run without CUDA."""
+    from audio_diffusion_b200._lib import B200ADError
+    from audio_diffusion_b200.training import EMAModel, FusedAdamW, mse_loss
+    from oracle.train_oracle import ema_decay
+
+    lin = torch.nn.Linear(4, 3)
+    ema = EMAModel(lin, inv_gamma=1.0, power=0.75, max_value=0.9999)
+    ref = [p.detach().clone() for p in lin.parameters()]
+    for step in range(1, 6):
+        with torch.no_grad():
+            for p in lin.parameters():
+                p.add_(0.1 * step)
+        ema.step(lin)                      # accepts a module or an iterable of parameters
+        d = ema_decay(step, 1.0, 0.75, 0.9999)
+        assert abs(ema.cur_decay_value - d) < 1e-12 and abs(ema.get_decay(step) - d) < 1e-12
+        for r, p in zip(ref, lin.parameters()):
+            r.sub_((1 - d) * (r - p.detach()))
+    for s, r in zip(ema.shadow_params, ref):
+        assert torch.allclose(s, r, rtol=1e-6, atol=1e-7)
+    before = [p._version for p in lin.parameters()]
+    ema.copy_to(lin.parameters())
+    assert all(torch.equal(p.detach(), s) for p, s in zip(lin.parameters(), ema.shadow_params))
+    assert all(p._version > v for p, v in zip(lin.parameters(), before))     # the engine keys its packed weights on this
+    if not torch.cuda.is_available():
+        opt = FusedAdamW(lin.parameters(), lr=1e-3)
+        for p in lin.parameters():
+            p.grad = torch.zeros_like(p)
+        with pytest.raises(B200ADError):
+            opt.step()
+        with pytest.raises(B200ADError):
+            mse_loss(torch.zeros(2), torch.zeros(2))
