@@ -117,7 +117,7 @@ def run_reference(args):
     if torch.get_num_threads() == 1 and (os.cpu_count() or 1) > 2:
         torch.set_num_threads(max(1, os.cpu_count() // 2))  # torchrun forces OMP_NUM_THREADS=1: use the physical cores
     cores = torch.get_num_threads()
-    batch, hw = 1, 256
+    batch, hw = 4, 256
     steps = max(1, min(args.steps, 3))
     warmup = 1
     val, dt = cpu_step_rate(batch, hw, steps, warmup)
@@ -274,9 +274,9 @@ def run_b200(args):
     cpu = None
     if not args.no_cpu and world == 1:
         cores = torch.get_num_threads()
-        v, dt = cpu_step_rate(1, HW, 2, 1)
+        v, dt = cpu_step_rate(4, HW, 3, 1)
         cpu = {"value": v, "unit": "mel-spectrograms/s", "cores": cores, "kind": "port",
-               "sample": f"batch 1 x 2 denoise steps (of 1000) at {HW}x{HW} on {cores} torch threads "
+               "sample": f"batch 4 x 3 denoise steps (of 1000) at {HW}x{HW} on {cores} torch threads "
                          f"({os.cpu_count()} cpus); oracle port of diffusers UNet2DModel + DDPMScheduler.step"}
     line = {
         "metric": "mel-spectrograms/sec (1000-step DDPM, 256x256x1)", "value": value, "unit": "mel-spectrograms/s",
