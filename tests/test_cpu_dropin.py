@@ -193,3 +193,49 @@ print('OK', rank)
     outs = [p.communicate(timeout=300) for p in procs]
     for p, (o, e) in zip(procs, outs):
         assert p.returncode == 0 and "OK" in o, o + e
+
+
+def test_pipeline_directory_round_trip(tmp_path):
+    """`pipeline.save_pretrained(dir)` / `AudioDiffusionPipeline.from_pretrained(dir)` (scripts/train_unet.py:106-111,
+    :302-303; audiodiffusion/__init__.py:30-32) in the diffusers directory layout — model_index.json, unet/, vqvae/,
+    scheduler/, mel/ — including a latent pipeline's AutoencoderKL and the deprecated attention key names of old hub files.
+    Host logic only (no kernels run)."""
+    import json
+
+    from safetensors.torch import load_file, save_file
+
+    from audio_diffusion_b200.mel import Mel
+    from audio_diffusion_b200.pipeline import AudioDiffusionPipeline
+    from audio_diffusion_b200.schedulers import DDIMScheduler
+    from audio_diffusion_b200.unet import UNet2DModel
+    from audio_diffusion_b200.vae import AutoencoderKL
+
+    unet = UNet2DModel(sample_size=(8, 8), in_channels=1, out_channels=1, layers_per_block=1, block_out_channels=(128, 128),
+                       down_block_types=("DownBlock2D", "AttnDownBlock2D"), up_block_types=("AttnUpBlock2D", "UpBlock2D"),
+                       seed=1)
+    vae = AutoencoderKL(in_channels=1, out_channels=1, down_block_types=("DownEncoderBlock2D",) * 2,
+                        up_block_types=("UpDecoderBlock2D",) * 2, block_out_channels=(128, 128), layers_per_block=1,
+                        latent_channels=1, seed=2)
+    pipe = AudioDiffusionPipeline(vqvae=vae, unet=unet, mel=Mel(x_res=16, y_res=16, hop_length=256), scheduler=DDIMScheduler())
+    d = str(tmp_path / "pipe")
+    pipe.save_pretrained(d)
+    idx = json.load(open(os.path.join(d, "model_index.json")))
+    assert idx["unet"][1] == "UNet2DModel" and idx["vqvae"][1] == "AutoencoderKL" and idx["scheduler"][1] == "DDIMScheduler"
+    # rewrite the U-Net weights with the deprecated attention names of older hub checkpoints
+    f = os.path.join(d, "unet", "diffusion_pytorch_model.safetensors")
+    sd = load_file(f)
+    ren = {".to_q.": ".query.", ".to_k.": ".key.", ".to_v.": ".value.", ".to_out.0.": ".proj_attn."}
+    old = {}
+    for k, v in sd.items():
+        for a, b in ren.items():
+            k = k.replace(a, b)
+        old[k] = v
+    assert any(".query." in k for k in old)
+    save_file(old, f)
+    back = AudioDiffusionPipeline.from_pretrained(d)
+    assert isinstance(back.scheduler, DDIMScheduler) and back.mel.x_res == 16 and back.mel.hop_length == 256
+    for k, v in unet.state_dict().items():
+        assert torch.equal(back.unet.state_dict()[k], v), k
+    for k, v in vae.state_dict().items():
+        assert torch.equal(back.vqvae.state_dict()[k], v), k
+    assert back.unet.sample_size in ((8, 8), [8, 8]) and back.vqvae.config["latent_channels"] == 1
