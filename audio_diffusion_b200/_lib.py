@@ -71,7 +71,7 @@ SYMBOLS = {
     "b200ad_unet_grad_offset": (_SZ, [_VP, _I]),
     "b200ad_unet_backward_bytes": (_SZ, [_VP]),
     "b200ad_unet_bind_backward": (_I, [_VP, _VP, _SZ, _VP, _VP]),
-    "b200ad_unet_backward": (_I, [_VP, _VP, _VP, _VP]),
+    "b200ad_unet_backward": (_I, [_VP, _VP, _VP, _I, _VP]),
     "b200ad_unet_backward_launch_count": (_I, [_VP]),
     "b200ad_vae_create": (_I, [C.POINTER(VAEConfigC), C.POINTER(_VP)]),
     "b200ad_vae_destroy": (None, [_VP]),

@@ -662,7 +662,7 @@ extern "C" int b200ad_unet_bind_backward(b200ad_unet* h, void* arena, size_t byt
   return 0;
 }
 
-extern "C" int b200ad_unet_backward(b200ad_unet* h, const float* x, const float* g_eps, void* stream) {
+extern "C" int b200ad_unet_backward(b200ad_unet* h, const float* x, const float* g_eps, int accumulate, void* stream) {
   if (!h || !h->bwd || h->bwd->ops.empty()) return set_err("bind_backward must be called before backward");
   if (!x || !g_eps) return set_err("backward: x and g_eps are required");
   Backward* bw = h->bwd;
@@ -677,7 +677,7 @@ extern "C" int b200ad_unet_backward(b200ad_unet* h, const float* x, const float*
     for (auto& e : ev) CK(cudaEventCreate(&e));
     CK(cudaEventRecord(ev[0], st));
   }
-  CK(cudaMemsetAsync(bw->grads, 0, bw->grad_floats * sizeof(float), st));
+  if (!accumulate) CK(cudaMemsetAsync(bw->grads, 0, bw->grad_floats * sizeof(float), st));   // every kernel below ADDS
   {
     std::vector<PackItem> items;
     items.reserve(bw->jobs.size());

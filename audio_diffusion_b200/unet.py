@@ -272,12 +272,20 @@ class UNet2DModel(nn.Module):
     def _backward_train(self, x: torch.Tensor, g: torch.Tensor):
         L = _lib.lib()
         g = g.to(torch.float32).contiguous()
+        # torch semantics: gradients accumulate until they are zeroed. p.grad is None (zero_grad(set_to_none=True), the
+        # default) -> start from zero; p.grad still our view (not zeroed, or zeroed in place) -> add to what is there.
+        views = getattr(self, "_grad_views", None)
+        params = [p for p in self.parameters() if p.requires_grad]
+        have = [p.grad is not None for p in params]
+        accumulate = bool(views) and all(have)
+        if any(have) and not accumulate:
+            raise _lib.B200ADError("UNet2DModel(b200): either all parameter gradients are set (accumulate) or none")
         with torch.cuda.device(x.device):
-            _lib.check(L.b200ad_unet_backward(self._h, x.data_ptr(), g.data_ptr(), _lib.stream_ptr()))
-        from .parallel import allreduce_mean_
-        allreduce_mean_(self._grad_flat)          # data parallel: one collective over the flat gradient buffer
-        # Parameter gradients are VIEWS of the flat buffer, assigned directly (no 700-tensor clone / accumulate pass): the
-        # reference zeroes gradients every iteration (train_unet.py:267); gradient_accumulation_steps > 1 is not supported.
+            _lib.check(L.b200ad_unet_backward(self._h, x.data_ptr(), g.data_ptr(), 1 if accumulate else 0, _lib.stream_ptr()))
+        if not getattr(self, "_no_sync", False):
+            from .parallel import allreduce_mean_
+            allreduce_mean_(self._grad_flat)      # data parallel: one collective over the flat gradient buffer
+        # Parameter gradients are VIEWS of the flat buffer, assigned directly (no 700-tensor clone / accumulate pass).
         if getattr(self, "_grad_views_key", None) != self._grad_flat.data_ptr():
             named = self._named()
             self._grad_views = []
@@ -288,9 +296,23 @@ class UNet2DModel(nn.Module):
             self._grad_views_key = self._grad_flat.data_ptr()
         for p, gv in self._grad_views:
             if p.grad is not None and p.grad.data_ptr() != gv.data_ptr():
-                raise _lib.B200ADError("UNet2DModel(b200): gradient accumulation across backward calls is not supported; "
-                                       "call optimizer.zero_grad(set_to_none=True) every iteration")
+                raise _lib.B200ADError("UNet2DModel(b200): p.grad must be None or the engine's own gradient view")
             p.grad = gv
+
+    def no_sync(self):
+        """Like `DistributedDataParallel.no_sync()`: backward passes inside the context skip the gradient all-reduce, so
+        micro-batches accumulate locally and the first backward outside it reduces the sum (`accelerator.accumulate`)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            old = getattr(self, "_no_sync", False)
+            self._no_sync = True
+            try:
+                yield
+            finally:
+                self._no_sync = old
+        return ctx()
 
     @property
     def last_backward_launch_count(self) -> int:

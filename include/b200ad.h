@@ -94,15 +94,16 @@ int b200ad_unet_last_launch_count(const b200ad_unet* h);
 
 /* ---- U-Net backward (scripts/train_unet.py:259 `accelerator.backward(loss)`) ----------------------------
  * Protocol: set_training(1) -> bind_workspace (every activation is kept) -> bind_backward -> per step: forward(x, t),
- * then backward(x, dL/d eps). Parameter gradients land in ONE flat fp32 buffer (zeroed by backward()); parameter i of the
+ * then backward(x, dL/d eps). Parameter gradients land in ONE flat fp32 buffer; parameter i of the
  * table lives at float offset b200ad_unet_grad_offset(h, i) — the Python mirror exposes them as `p.grad` views. */
 int b200ad_unet_set_training(b200ad_unet* h, int on);
 size_t b200ad_unet_grad_floats(b200ad_unet* h);
 size_t b200ad_unet_grad_offset(b200ad_unet* h, int i);
 size_t b200ad_unet_backward_bytes(b200ad_unet* h);       /* arena for activation gradients, temporaries, transposed weights */
 int b200ad_unet_bind_backward(b200ad_unet* h, void* arena, size_t bytes, float* grads, void* stream);
-/* x: the forward input [N, 1, H, W]; g_eps: gradient of the loss w.r.t. the forward output, fp32 [N, 1, H, W]. */
-int b200ad_unet_backward(b200ad_unet* h, const float* x, const float* g_eps, void* stream);
+/* x: the forward input [N, 1, H, W]; g_eps: gradient of the loss w.r.t. the forward output, fp32 [N, 1, H, W].
+ * accumulate = 0 zeroes the gradient buffer first; != 0 adds to it (gradient accumulation, `accelerator.accumulate`). */
+int b200ad_unet_backward(b200ad_unet* h, const float* x, const float* g_eps, int accumulate, void* stream);
 int b200ad_unet_backward_launch_count(const b200ad_unet* h);
 
 /* ---- Latent autoencoder: replaces diffusers.AutoencoderKL as the pipeline drives it ---------------------

@@ -224,3 +224,24 @@ def test_ema_copy_to_refreshes_packed_weights(cuda):
         ema.copy_to(m.parameters())
         b = m(x, 10)["sample"].clone()
     assert (a - b).abs().max() > 1e-3 * a.abs().max()
+
+
+def test_gradient_accumulation_equals_full_batch(cuda):
+    """`accelerator.accumulate(model)` (scripts/train_unet.py:252): two micro-batches with loss / 2 each, gradients left in
+    place between the backward calls, give the gradient of the full batch (GroupNorm is per sample)."""
+    from audio_diffusion_b200.unet import UNet2DModel
+    model = UNet2DModel(sample_size=(32, 32), seed=3, **TRAIN_CFG).to(cuda).train()
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 1, 32, 32, generator=g).to(cuda)
+    tgt = torch.randn(2, 1, 32, 32, generator=g).to(cuda)
+    t = torch.tensor([100, 650]).to(cuda)
+    torch.nn.functional.mse_loss(model(x, t)["sample"], tgt).backward()
+    full = model._grad_flat.clone()
+    for p in model.parameters():
+        p.grad = None
+    with model.no_sync():
+        (torch.nn.functional.mse_loss(model(x[:1], t[:1])["sample"], tgt[:1]) / 2).backward()
+    (torch.nn.functional.mse_loss(model(x[1:], t[1:])["sample"], tgt[1:]) / 2).backward()
+    acc = model._grad_flat
+    rel = ((acc - full).norm() / full.norm()).item()
+    assert rel < 2e-3, rel
