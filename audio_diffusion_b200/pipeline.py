@@ -229,7 +229,10 @@ class AudioDiffusionPipeline(DiffusionPipeline):
                 self.unet.sample_size[1] * self.mel.get_sample_rate() / self.mel.x_res / self.mel.hop_length)
             mask_start = int(mask_start_secs * pixels_per_second)
             mask_end = int(mask_end_secs * pixels_per_second)
-            mask = self.scheduler.add_noise(input_images, noise, torch.tensor(self.scheduler.timesteps[start_step:]))
+            # The reference's `images = noise` ALIASES the two tensors (:131), so the assignment above also rewrites
+            # noise[0, 0] and the mask below is built from that modified noise. `images` (a private copy here, because the
+            # fused step updates it in place) holds exactly those values at this point.
+            mask = self.scheduler.add_noise(input_images, images, torch.tensor(self.scheduler.timesteps[start_step:]))
 
         fused = isinstance(self.unet, UNet2DModel) and hasattr(self.scheduler, "step_coef")
         is_ddim = isinstance(self.scheduler, DDIMScheduler)
@@ -264,9 +267,9 @@ class AudioDiffusionPipeline(DiffusionPipeline):
                    else map(lambda _: Image.fromarray(_, mode="RGB").convert("L"), host))
         if not return_audio:
             return pil
-        if host.shape[3] == 1:
-            audios = list(self.mel.images_to_audio(u8[:, 0]))
-        else:
+        if host.shape[3] == 1 and hasattr(self.mel, "images_to_audio"):
+            audios = list(self.mel.images_to_audio(u8[:, 0]))          # batched Griffin-Lim (the engine's Mel)
+        else:                                                          # any object with the reference Mel's surface (:201)
             audios = list(map(lambda _: self.mel.image_to_audio(_), pil))
         if not return_dict:
             return pil, (self.mel.get_sample_rate(), audios)

@@ -239,3 +239,63 @@ def test_pipeline_directory_round_trip(tmp_path):
     for k, v in vae.state_dict().items():
         assert torch.equal(back.vqvae.state_dict()[k], v), k
     assert back.unet.sample_size in ((8, 8), [8, 8]) and back.vqvae.config["latent_channels"] == 1
+
+
+class ScriptedMel(FakeMel):
+    """FakeMel plus the audio-conditioning surface (`load_audio`, `audio_slice_to_image`) with a fixed image."""
+
+    def load_audio(self, audio_file=None, raw_audio=None):
+        self.loaded = True
+
+    def audio_slice_to_image(self, slice):
+        from PIL import Image
+        rng = np.random.default_rng(5)
+        return Image.fromarray(rng.integers(0, 256, (self.y_res, self.x_res), dtype=np.uint8))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not present (GPU box)")
+@pytest.mark.parametrize("sched", ["ddpm", "ddim"])
+def test_mirrored_pipeline_equals_reference_pipeline_on_cpu(sched):
+    """The product's own `AudioDiffusionPipeline.__call__` (audio_diffusion_b200/pipeline.py) against the reference's
+    unchanged file for the audio-conditioned / in-painting path (`raw_audio`, `start_step`, `mask_start_secs`,
+    `mask_end_secs`, pipeline_audio_diffusion.py:133-185): identical uint8 images. Both drive the CPU oracle U-Net (the mirror
+    then takes its unfused branch); only the mirror's float->uint8 CUDA kernel is replaced by the same torch expression."""
+    code = f"""
+import sys
+sys.path[:0] = [{ROOT!r}, {os.path.join(ROOT, 'audio_diffusion_b200', 'compat')!r}, {REF!r}, {os.path.join(ROOT, 'tests')!r}]
+import torch, numpy as np
+from audiodiffusion.pipeline_audio_diffusion import AudioDiffusionPipeline as RefPipe   # byte-identical reference file
+from audio_diffusion_b200.pipeline import AudioDiffusionPipeline as Mirror
+from diffusers import DDPMScheduler, DDIMScheduler
+from test_cpu_dropin import OracleUNet, ScriptedMel
+Mirror.images_to_u8 = staticmethod(lambda x: ((x / 2 + 0.5).clamp(0, 1) * 255).round().to(torch.uint8))
+is_ddim = {sched!r} == 'ddim'
+outs = []
+for cls in (RefPipe, Mirror):
+    pipe = cls(vqvae=None, unet=OracleUNet(), mel=ScriptedMel(), scheduler=(DDIMScheduler() if is_ddim else DDPMScheduler()))
+    pipe.set_progress_bar_config(disable=True)
+    noise = torch.randn(1, 1, 16, 16, generator=torch.Generator().manual_seed(3))   # the reference's start_step path is batch-1 only (:150)
+    kw = dict(batch_size=1, raw_audio=np.zeros(16 * 512 * 2, dtype=np.float32), slice=0, start_step=2, steps=6, noise=noise,
+              step_generator=torch.Generator().manual_seed(4), mask_start_secs=0.05, mask_end_secs=0.05, return_dict=False)
+    if is_ddim:
+        kw['eta'] = 0.5
+    images, (sr, audios) = pipe(**kw)
+    outs.append(np.stack([np.asarray(im) for im in images]))
+    assert sr == 22050 and len(audios) == 1
+assert outs[0].shape == (1, 16, 16) and np.array_equal(outs[0], outs[1]), np.abs(outs[0].astype(int) - outs[1].astype(int)).max()
+if is_ddim:   # DDIM inversion (`encode`, :207-242) and `slerp` (:244-263): same numbers from both files
+    from PIL import Image
+    rng = np.random.default_rng(9)
+    pil = [Image.fromarray(rng.integers(0, 256, (16, 16), dtype=np.uint8)) for _ in range(2)]
+    encs = []
+    for cls in (RefPipe, Mirror):
+        pipe = cls(vqvae=None, unet=OracleUNet(), mel=ScriptedMel(), scheduler=DDIMScheduler())
+        pipe.set_progress_bar_config(disable=True)
+        encs.append(pipe.encode(pil, steps=5))
+    assert encs[0].shape == (2, 1, 16, 16) and torch.equal(encs[0], encs[1])
+    a, b = torch.randn(4, 4, generator=torch.Generator().manual_seed(1)), torch.randn(4, 4, generator=torch.Generator().manual_seed(2))
+    assert torch.equal(RefPipe.slerp(a, b, 0.3), Mirror.slerp(a, b, 0.3))
+print('ok')
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
