@@ -299,3 +299,32 @@ print('ok')
 """
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not present (GPU box)")
+def test_mel_host_logic_equals_reference_mel():
+    """Slicing / padding / resolution bookkeeping of the engine's `Mel` against the reference's own `audiodiffusion/mel.py`
+    class (imported unchanged through the shim; its librosa-backed transforms are not called): mel.py:80-133."""
+    code = f"""
+import sys
+sys.path[:0] = [{ROOT!r}, {os.path.join(ROOT, 'audio_diffusion_b200', 'compat')!r}, {REF!r}]
+import numpy as np
+from audiodiffusion.mel import Mel as RefMel          # byte-identical reference file
+from audio_diffusion_b200.mel import Mel
+rng = np.random.default_rng(0)
+for (x_res, y_res, hop) in [(256, 256, 512), (64, 64, 1024), (96, 32, 256)]:
+    for n in [10, x_res * hop - 1, x_res * hop, 3 * x_res * hop + 17]:
+        a, b = RefMel(x_res=x_res, y_res=y_res, hop_length=hop), Mel(x_res=x_res, y_res=y_res, hop_length=hop)
+        audio = rng.standard_normal(n).astype(np.float32)
+        a.load_audio(raw_audio=audio.copy()); b.load_audio(raw_audio=audio.copy())
+        assert a.slice_size == b.slice_size and a.n_mels == b.n_mels and a.get_sample_rate() == b.get_sample_rate()
+        assert a.get_number_of_slices() == b.get_number_of_slices(), (x_res, n)
+        assert len(a.audio) == len(b.audio) and a.audio.dtype == b.audio.dtype and np.array_equal(a.audio, b.audio)
+        for s in range(a.get_number_of_slices()):
+            assert np.array_equal(a.get_audio_slice(s), b.get_audio_slice(s))
+    a.set_resolution(32, 16); b.set_resolution(32, 16)
+    assert (a.x_res, a.y_res, a.n_mels, a.slice_size) == (b.x_res, b.y_res, b.n_mels, b.slice_size)
+print('ok')
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
