@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200ad.so")
+# B200AD_LIB: development override used for kernel A/B builds (csrc/Makefile EXTRA=...); the product loads libb200ad.so
+LIB_PATH = os.environ.get("B200AD_LIB") or os.path.join(_HERE, "libb200ad.so")
 
 MAX_BLOCKS = 8
 

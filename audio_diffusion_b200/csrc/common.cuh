@@ -31,6 +31,13 @@ __host__ __device__ inline Geom make_geom(int N, int H, int W) {
   return g;
 }
 
+// TMEM lane (= row of the packed weight tile) -> output channel within the 128-channel tile.  Within every 32-lane
+// quarter the lanes are interleaved so that the four lanes 4c .. 4c+3 hold channel c of four different 8-channel planes:
+// the epilogue's `stmatrix.trans` then writes a complete PF8 vector (8 channels of one pixel) per 16-byte row.
+__host__ __device__ constexpr int conv_lane_channel(int lane128) {
+  return (lane128 & ~31) | ((lane128 & 3) << 3) | ((lane128 >> 2) & 7);
+}
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -88,6 +95,20 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
       ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// 1-D shared -> global bulk store (TMA engine), tracked by the issuing thread's bulk async-group.
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed groups of this thread have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have completed (writes performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// named barrier among `nthreads` threads (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
@@ -218,6 +239,47 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
+}
+
+// ---------------------------------------------------------- packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2)
+// Two independent fp32 lanes in one 64-bit register pair: one issue slot for two results.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 f2_unpack(f32x2_t v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// bf16x2 (lo = first element) -> packed fp32 pair: a shift and a mask, exact
+__device__ __forceinline__ f32x2_t f2_from_bf16x2(uint32_t u) {
+  return f2_pack(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t f2_to_bf16x2(f32x2_t v) {   // round to nearest even, lo half = first element
+  const float2 f = f2_unpack(v);
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(f.y), "f"(f.x));
+  return r;
+}
+
+// Four 8x8 b16 matrices, transposed store: row r of matrix m is written as 16 bytes at the address supplied by lane
+// 8m + r; its element c comes from lane 4c + (r >> 1), half (r & 1) of that lane's register m.
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t saddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};"
+               ::"r"(saddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
 #endif  // __CUDACC__
 

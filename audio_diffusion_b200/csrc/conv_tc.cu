@@ -3,25 +3,34 @@
 //
 // GEMM view (transposed): D^T[cout, pixel] = sum over (segment, tap, cin) W[cout, cin, tap] * X[pixel + shift(tap), cin].
 //   M = 128 output channels (weights are the A operand), N = up to 256 output pixels (activations are the B operand),
-//   K = 16 input channels per tcgen05.mma.  Why this way round: the kernel is bound by SHARED-MEMORY bandwidth — with
+//   K = 16 input channels per tcgen05.mma.  Why this way round: the kernel is bound by SHARED-MEMORY bandwidth - with
 //   M = N = 128 the two operand reads alone need the full 128 B/clk; N = 256 reads 12 KB per 128-cycle MMA (96 B/clk),
 //   halves the number of MMAs to issue, and the weights of one tap stay latched in the A collector (.collector::a::fill /
 //   ::lastuse) while the second pixel group is multiplied.
 // Pixel operand: the PF8 layout stores 8-channel vectors of consecutive pixels contiguously, which *is* the K-major
-//   no-swizzle UMMA core-matrix layout (8 rows x 16 B). A work item covers MAXG*128 consecutive flat pixels; per 16 input
+//   no-swizzle UMMA core-matrix layout (8 rows x 16 B). A work item covers 4 x 128 consecutive flat pixels; per 16 input
 //   channels ONE contiguous window per 8-channel plane (the run plus a halo of Wp+1 pixels on both sides) is bulk-copied
 //   (TMA engine, UBLKCP) into shared memory, and every tap is a descriptor whose start address is shifted by
 //   (dh*Wp + dw) * 16 B.  (Measured: a bulk copy costs ~130 cycles of TMA time however small it is -> few large copies.)
 // Fused GroupNorm(+SiLU): the windows hold the RAW producer output; five transform warps rewrite them in place
 //   (x * scale[n][c] + shift[n][c], SiLU via one tanh.approx, zero on pad/guard positions) between the TMA landing and
-//   the MMA reading them, so the normalised tensor never exists in HBM.
+//   the MMA reading them, so the normalised tensor never exists in HBM.  The work is split 2:2:2:1:1 over the warps so
+//   that each SM sub-partition (scheduler + MUFU) carries a quarter of it.
 // Weights: pre-packed on the device into per-(cout tile, 16-channel step, tap) 4 KB blocks; a separate, finer ring
 //   (CONV_BT taps per slot) with its own producer warp.
 // Residual adds are an extra 1-tap K-segment with identity weights (exact, and no epilogue loads).
-// Accumulators: 128 lanes (cout) x MAXG*128 fp32 columns (pixels) in TMEM, ACC stages (see ConvCfg).
+// Accumulators: 128 lanes (cout) x 512 fp32 columns (pixels) in TMEM = all of it, handled as two 256-column HALVES with
+//   their own full/empty barriers.  The first and the last k-step of an item are issued half by half (all taps into
+//   columns 0-255, then all taps into 256-511) instead of tap by tap, so half 0 is complete one k-step's worth of MMAs
+//   before half 1, and the next item may start on half 0 while half 1 is still being drained: the epilogue of item i
+//   overlaps the tail of item i and the head of item i+1 (it was fully exposed, 7 of 34 ms per step, in round 1).
+// Epilogue (8 warps, ~2.7 instructions per element instead of ~7): TMEM -> registers (32x32b: thread = channel, 32
+//   pixels) -> +bias/temb and GroupNorm partial sums on packed fp32 pairs (FADD2/FFMA2) -> cvt.rn.bf16x2 -> four
+//   stmatrix.x4.trans per 32-pixel chunk.  The packed weight rows are interleaved (conv_lane_channel) so that a
+//   transposed 8x8 store lands exactly one PF8 vector (8 channels of one pixel) per 16-byte row -> coalesced 16-byte
+//   global stores, pad columns predicated off.
 // Warp roles (16 warps): 0 activation producer, 1 MMA issuer (uniform datapath, one elected lane), 3 weight producer,
-//   2/8-11 transform (warp 2 also owns the TMEM allocation), 4-7 + 12-15 epilogue: TMEM -> +bias/temb -> per-channel GroupNorm
-//   partial sums (thread-local) -> bf16 -> 32x32 transpose through shared memory -> coalesced 16-byte PF8 stores.
+//   2/8-11 transform (warp 2 also owns the TMEM allocation), 4-7 + 12-15 epilogue.
 #include <cstdlib>
 
 #include "conv_tc.cuh"
@@ -30,8 +39,9 @@ namespace b200ad {
 
 constexpr int CONV_THREADS = 512;     // 16 warps
 constexpr int CONV_XF_THREADS = 160;  // transform warps 2, 8, 9, 10, 11
-constexpr int CONV_TROW = 80;         // bytes per pixel row of the epilogue transpose tile (32 ch bf16 + 16 B pad)
-constexpr int CONV_TTILE = 32 * CONV_TROW;
+constexpr int CONV_HALF = 2 * CONV_TM;      // pixels per epilogue half (256 accumulator columns)
+constexpr int CONV_SPLANE = CONV_HALF * 16 + 32;  // epilogue staging: bytes per 8-channel plane (256 pixels x 16 B, +32 B bank skew)
+constexpr int CONV_STAGING = 16 * CONV_SPLANE;    // one half item: 16 planes (128 channels) x 256 pixels, bf16
 
 struct WorkItem {
   int n, ntile, m0, G;
@@ -43,43 +53,41 @@ __device__ __forceinline__ WorkItem decode_work(const ConvParams& p, int w) {
   const int gidx = w / p.ntiles_n;
   wi.n = gidx / p.groups_per_img;
   const int g = gidx - wi.n * p.groups_per_img;
-  wi.m0 = g * (p.maxg * CONV_TM);
+  wi.m0 = g * (CONV_MAXG * CONV_TM);
   const int rem = p.H * p.Wp - wi.m0;
-  wi.G = min(p.maxg, (rem + CONV_TM - 1) / CONV_TM);
+  wi.G = min(CONV_MAXG, (rem + CONV_TM - 1) / CONV_TM);
   return wi;
 }
 
-// one 16-byte vector (8 channels of one pixel): affine + optional SiLU in fp32, back to bf16.
+// one 16-byte vector (8 channels of one pixel): affine + optional SiLU in fp32 (packed pairs), back to bf16.
 // With SiLU the caller passes HALVED scale/shift: h = a/2 = x*s' + t', silu(a) = a * (0.5 + 0.5 tanh(a/2)) = h + h * tanh(h)
-// -> FFMA, MUFU.TANH, FFMA per element.
+// -> per two elements: FFMA2, 2 MUFU.TANH, FFMA2.
 template <bool SILU>
-__device__ __forceinline__ uint4 xform_vec(uint4 v, const float2 (&ss)[8]) {
+__device__ __forceinline__ uint4 xform_vec(uint4 v, const f32x2_t (&sc)[4], const f32x2_t (&sh)[4]) {
   uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    const float2 f = unpack_bf16x2(u[e]);
-    float a = fmaf(f.x, ss[2 * e].x, ss[2 * e].y);
-    float b = fmaf(f.y, ss[2 * e + 1].x, ss[2 * e + 1].y);
+    f32x2_t a = f2_fma(f2_from_bf16x2(u[e]), sc[e], sh[e]);
     if (SILU) {
-      a = fmaf(a, tanh_approx(a), a);
-      b = fmaf(b, tanh_approx(b), b);
+      const float2 f = f2_unpack(a);
+      a = f2_fma(a, f2_pack(tanh_approx(f.x), tanh_approx(f.y)), a);
     }
-    u[e] = pack_bf16x2(a, b);
+    u[e] = f2_to_bf16x2(a);
   }
   return make_uint4(u[0], u[1], u[2], u[3]);
 }
 
-template <int MAXG, int ACC, int AS, int BS>
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+  constexpr int AS = CONV_AS, BS = CONV_BS;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int a_bytes = p.a_stage;
 
   uint8_t* bring = smem + AS * a_bytes;                 // weight ring
-  uint8_t* ttile = bring + BS * CONV_B_SLOT;            // 8 epilogue transpose tiles (one per epilogue warp)
-  uint8_t* ctrl = ttile + 8 * CONV_TTILE;
-  // barriers: fullA[AS], readyA[AS], emptyA[AS], fullB[BS], emptyB[BS], tmem_full[ACC], tmem_empty[ACC]
+  uint8_t* stg = bring + BS * CONV_B_SLOT;              // epilogue staging: [16 planes][256 px][16 B] of one half item
+  uint8_t* ctrl = stg + CONV_STAGING;
+  // barriers: fullA[AS], readyA[AS], emptyA[AS], fullB[BS], emptyB[BS], tmem_full, tmem_empty
   uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctrl + 504);
   const uint32_t smem_base = smem_u32(smem);
@@ -90,8 +98,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
   const uint32_t bar_fullB = smem_u32(bars + 3 * AS);
   const uint32_t bar_emptyB = smem_u32(bars + 3 * AS + BS);
   const uint32_t bar_tfull = smem_u32(bars + 3 * AS + 2 * BS);
-  const uint32_t bar_tempty = smem_u32(bars + 3 * AS + 2 * BS + ACC);
-  static_assert((3 * AS + 2 * BS + 2 * ACC) * 8 <= 504, "barrier block overflows");
+  const uint32_t bar_tempty = smem_u32(bars + 3 * AS + 2 * BS + 1);
+  static_assert((3 * AS + 2 * BS + 2) * 8 <= 504, "barrier block overflows");
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < AS; ++s) {
@@ -103,10 +111,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
       mbar_init(bar_fullB + 8 * s, 1);
       mbar_init(bar_emptyB + 8 * s, 1);
     }
-    for (int a = 0; a < ACC; ++a) {
-      mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 256);
-    }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tempty, 256);
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -119,6 +125,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
     // ================================ activation producer: per k-step two windows (one per 8-channel plane), lanes 0 / 1
     int stage = 0;
     uint32_t phase = 0;
+    if (p.dbg & 4) {   // experiment: start the CTAs out of phase so that their epilogue store bursts do not coincide
+      const long long t0 = clock64(), wait = (long long)(blockIdx.x & 7) * 2304;
+      while (clock64() - t0 < wait) {}
+    }
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const WorkItem wi = decode_work(p, w);
       for (int s = 0; s < p.nseg; ++s) {
@@ -151,7 +161,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
         const int ntile = w % p.ntiles_n;
         for (int s = 0; s < p.nseg; ++s) {
           const ConvSeg& sg = p.seg[s];
-          const char* src = reinterpret_cast<const char*>(sg.wpack + (long long)ntile * sg.ksteps * sg.ntaps * (CONV_B_TAP / 2));
+          const char* src = reinterpret_cast<const char*>(sg.wpack + (long long)ntile * sg.wtile_stride);
           for (int ks = 0; ks < sg.ksteps; ++ks) {
             for (int t0 = 0; t0 < sg.ntaps; t0 += CONV_BT) {
               const uint32_t bytes = (uint32_t)min(CONV_BT, sg.ntaps - t0) * CONV_B_TAP;
@@ -173,16 +183,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
     constexpr uint64_t desc_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, descriptor version 1
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
-    int item = 0;
+    uint32_t item = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++item) {
       const WorkItem wi = decode_work(p, w);
-      const int acc = item % ACC;
-      const uint32_t d0 = tmem_base + (uint32_t)acc * (MAXG * CONV_TM);
+      const uint32_t d0 = tmem_base;
       // pixel groups: [0, n0) with one MMA of N = n0 (<= 256) and, if the item has more than two tiles, [256, 256 + n1)
       const int n0 = min(wi.G, 2) * CONV_TM, n1 = (wi.G - 2) * CONV_TM;
       const uint32_t idesc0 = (n0 == 256) ? idesc256 : make_idesc_bf16(CONV_NT, CONV_TM);
       const uint32_t idesc1 = (n1 == 256) ? idesc256 : make_idesc_bf16(CONV_NT, CONV_TM);
-      mbar_wait_warp(bar_tempty + 8 * acc, (((uint32_t)(item / ACC)) & 1) ^ 1);  // epilogue drained this accumulator
+      mbar_wait_warp(bar_tempty, (item & 1) ^ 1);  // the epilogue has moved the previous item out of TMEM
       tc_fence_after();
       uint32_t fresh = 1;  // first k-step of the item overwrites the accumulators
       for (int s = 0; s < p.nseg; ++s) {
@@ -205,7 +214,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
                 const uint32_t accum = (fresh && t0 + t == 0) ? 0u : 1u;
                 if (n1 > 0) {  // two pixel groups share the weights: latch them in the A collector
                   umma_bf16_afill(d0, wdesc, desc_hi | (uint64_t)x_lo, idesc0, accum);
-                  umma_bf16_alast(d0 + 256, wdesc, desc_hi | (uint64_t)(x_lo + (256 * 16 >> 4)), idesc1, accum);
+                  umma_bf16_alast(d0 + CONV_HALF, wdesc, desc_hi | (uint64_t)(x_lo + (CONV_HALF * 16 >> 4)), idesc1, accum);
                 } else {
                   umma_bf16(d0, wdesc, desc_hi | (uint64_t)x_lo, idesc0, accum);
                 }
@@ -220,39 +229,45 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
           if (++sa == AS) { sa = 0; pa ^= 1; }
         }
       }
-      umma_commit_elect(bar_tfull + 8 * acc);
+      umma_commit_elect(bar_tfull);
     }
   } else if ((warp >= 4 && warp < 8) || warp >= 12) {
-    // ================================ epilogue (8 warps). TMEM lane = output channel, column = pixel. Two warps share a
-    // TMEM lane quarter and take alternate 32-pixel chunks.
+    // ================================ epilogue (8 warps). TMEM lane = output channel (interleaved, conv_lane_channel),
+    // column = pixel. The item leaves TMEM in two halves of 256 pixels: registers -> bf16 -> transposed into the 64 KB
+    // staging buffer as finished PF8 runs ([plane][pixel][8 ch]) -> ONE bulk store (TMA engine) per plane and half.
+    // The accumulators are released as soon as the last TMEM load has landed; the global stores (4.9 of the 6.8 ms/step the
+    // round-1 epilogue exposed: st.global from 8 warps moves ~20 B/clk/SM) drain behind the next item's MMAs.
+    // Two warps share a TMEM lane quarter (= 4 planes) and take alternate 32-pixel chunks; they meet on a named barrier.
     const int q = warp & 3;                  // TMEM lane quarter = channels [32q, 32q + 32) of this cout tile
-    const int half = warp >> 3;              // 0: warps 4-7 (even chunks), 1: warps 12-15 (odd chunks)
-    uint8_t* tile = ttile + (half * 4 + q) * CONV_TTILE;
+    const int par = warp >> 3;               // 0: warps 4-7 (even chunks), 1: warps 12-15 (odd chunks)
+    const uint32_t stg_q = smem_u32(stg) + (uint32_t)(4 * q * CONV_SPLANE);    // this quarter's 4 planes
+    // stmatrix row address of this lane: matrix m = lane >> 3 holds pixel pair m of a group of 8 pixels, row r = lane & 7
+    // is (pixel 2m + (r & 1), plane r >> 1)
+    const uint32_t st_addr = stg_q + (uint32_t)(((lane & 7) >> 1) * CONV_SPLANE + (2 * (lane >> 3) + (lane & 1)) * 16);
     const Geom og = make_geom(p.N, p.up2 ? 2 * p.H : p.H, p.up2 ? 2 * p.W : p.W);   // geometry of the output tensor
     const long long out_img_stride = (long long)(p.cout >> 3) * og.PL * 8;
     const int hw_end = p.H * p.Wp;
     const bool do_stats = p.stats != nullptr;
-    int item = 0;
+    const bool issuer = par == 0 && lane < 4;         // lane g of warp (q, 0) stores plane 4q + g
+    const int cw = ((lane & 3) << 3) | (lane >> 2);   // this lane's channel within the warp's 32 (conv_lane_channel)
+    uint32_t item = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++item) {
       const WorkItem wi = decode_work(p, w);
-      const int acc = item % ACC;
-      const uint32_t acc_col = (uint32_t)acc * (MAXG * CONV_TM);
-      const int c = wi.ntile * CONV_NT + q * 32 + lane;   // this thread's output channel
+      const int c = wi.ntile * CONV_NT + q * 32 + cw;   // this thread's output channel
       float bias = p.bias ? __ldg(p.bias + c) : 0.f;
       if (p.temb) bias += __ldg(p.temb + (long long)wi.n * p.temb_stride + c);
-      // the four 8-channel planes this warp writes; each lane stores one pixel (16 B) per plane per 32-pixel chunk
+      const f32x2_t bias2 = f2_pack(bias, bias);
+      // the four 8-channel planes this warp pair writes
       __nv_bfloat16* out_pl = p.out + (long long)wi.n * out_img_stride + (long long)(wi.ntile * 16 + q * 4) * og.PL * 8;
 
-      mbar_wait(bar_tfull + 8 * acc, ((uint32_t)(item / ACC)) & 1);
-      tc_fence_after();
-
-      float ssum = 0.f, ssq = 0.f;
+      f32x2_t ssum2 = 0ull, ssq2 = 0ull;     // (even pixel, odd pixel) partial sums of this thread's channel
       const int nchunk = (p.dbg & 8) ? 0 : wi.G * (CONV_TM / 32);
-      const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16) + acc_col;
-      // one 32-pixel chunk: +bias, statistics, bf16, transpose through the warp's tile, 16-byte PF8 stores
-      auto process = [&](const uint32_t (&r)[32], int jc) {
+      const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16);
+      // one 32-pixel chunk: +bias, statistics, bf16, transposed store into the staging buffer at pixel offset `spx`
+      auto process = [&](const uint32_t (&r)[32], int jc, int spx) {
         const int mc = wi.m0 + jc * 32;
-        // validity mask of the chunk's 32 pixels (pad columns and the run-off behind the image are not stored / counted)
+        // validity mask of the chunk's 32 pixels: pad columns and the run-off behind the image are written as ZEROS (they
+        // are zero guards of the layout) and do not count for the statistics
         uint32_t mask;
         {
           const int nvalid = min(32, max(0, hw_end - mc));
@@ -268,73 +283,118 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
             }
           }
         }
+        uint32_t pk[16];
         if (mask == 0xffffffffu) {   // common case: no per-element predicate
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float v = __uint_as_float(r[e]) + bias;
-            ssum += v; ssq = fmaf(v, v, ssq);
-            *reinterpret_cast<__nv_bfloat16*>(tile + e * CONV_TROW + lane * 2) = __float2bfloat16_rn(v);
+          for (int j = 0; j < 16; ++j) {
+            const f32x2_t v = f2_add(f2_pack(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), bias2);
+            ssum2 = f2_add(ssum2, v);
+            ssq2 = f2_fma(v, v, ssq2);
+            pk[j] = f2_to_bf16x2(v);
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float v = __uint_as_float(r[e]) + bias;
-            if ((mask >> e) & 1) { ssum += v; ssq = fmaf(v, v, ssq); }
-            *reinterpret_cast<__nv_bfloat16*>(tile + e * CONV_TROW + lane * 2) = __float2bfloat16_rn(v);
+          for (int j = 0; j < 16; ++j) {
+            const f32x2_t v = f2_add(f2_pack(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), bias2);
+            const float2 f = f2_unpack(v);
+            const f32x2_t vm = f2_pack(((mask >> (2 * j)) & 1) ? f.x : 0.f, ((mask >> (2 * j + 1)) & 1) ? f.y : 0.f);
+            ssum2 = f2_add(ssum2, vm);
+            ssq2 = f2_fma(vm, vm, ssq2);
+            pk[j] = f2_to_bf16x2(vm);
           }
         }
-        __syncwarp();
-        if ((mask >> lane) & 1) {
-          long long pix;
-          if (p.up2) {  // scatter into the 2x tensor at this launch's parity
-            const int m = mc + lane, hh = m / p.Wp, ww = m - hh * p.Wp;
-            pix = (long long)(og.lead + (2 * hh + p.oy) * og.Wp + 2 * ww + p.ox) * 8;
-          } else {
-            pix = (long long)(p.lead + mc + lane) * 8;
-          }
+        const uint32_t sa = st_addr + (uint32_t)spx * 16u;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint4 o = *reinterpret_cast<const uint4*>(tile + lane * CONV_TROW + g * 16);
-            *reinterpret_cast<uint4*>(out_pl + (long long)g * og.PL * 8 + pix) = o;
+        for (int k = 0; k < 4; ++k) stmatrix_x4_trans(sa + 128u * k, pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+        if (p.up2) {   // folded upsample: scatter into the 2x tensor at this launch's parity, straight from the staging rows
+          __syncwarp();
+          if (((mask >> lane) & 1) && !(p.dbg & 2)) {
+            const int m = mc + lane, hh = m / p.Wp, ww = m - hh * p.Wp;
+            const long long pix = (long long)(og.lead + (2 * hh + p.oy) * og.Wp + 2 * ww + p.ox) * 8;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 o = *reinterpret_cast<const uint4*>(stg + (4 * q + g) * CONV_SPLANE + (spx + lane) * 16);
+              *reinterpret_cast<uint4*>(out_pl + (long long)g * og.PL * 8 + pix) = o;
+            }
+          }
+          __syncwarp();
+        }
+      };
+      const int nhalf = (wi.G > 2) ? 2 : 1;
+#pragma unroll 1
+      for (int h = 0; h < nhalf; ++h) {
+        if (!p.up2) {   // the bulk stores of the previous half must have finished READING the staging planes of this quarter
+          if (issuer) bulk_wait_read_all();
+          __syncwarp();
+          named_bar_sync(1 + q, 64);
+        }
+        if (h == 0) {
+          mbar_wait(bar_tfull, item & 1);
+          tc_fence_after();
+        }
+        const int jbeg = 8 * h, jend = min(nchunk, 8 * h + 8);
+        {
+          // two register sets: the TMEM load of this warp's next chunk is in flight while the current one is processed;
+          // with the up2 scatter every chunk reuses the warp's own 32-pixel window of the staging planes
+          uint32_t ra[32], rb[32];
+          int jc = jbeg + par;
+          if (jc < jend) { tmem_ld32(tsrc + (uint32_t)(jc * 32), ra); tmem_ld_wait(); }
+          while (jc < jend) {
+            if (jc + 2 < jend) tmem_ld32(tsrc + (uint32_t)((jc + 2) * 32), rb);
+            process(ra, jc, p.up2 ? par * 32 : (jc - jbeg) * 32);
+            tmem_ld_wait();
+            jc += 2;
+            if (jc >= jend) break;
+            if (jc + 2 < jend) tmem_ld32(tsrc + (uint32_t)((jc + 2) * 32), ra);
+            process(rb, jc, p.up2 ? par * 32 : (jc - jbeg) * 32);
+            tmem_ld_wait();
+            jc += 2;
           }
         }
-        __syncwarp();
-      };
-      // two register sets: the TMEM load of this warp's next chunk is in flight while the current one is processed
-      uint32_t ra[32], rb[32];
-      int jc = half;
-      if (jc < nchunk) { tmem_ld32(tsrc + (uint32_t)(jc * 32), ra); tmem_ld_wait(); }
-      while (jc < nchunk) {
-        if (jc + 2 < nchunk) tmem_ld32(tsrc + (uint32_t)((jc + 2) * 32), rb);
-        process(ra, jc);
-        tmem_ld_wait();
-        jc += 2;
-        if (jc >= nchunk) break;
-        if (jc + 2 < nchunk) tmem_ld32(tsrc + (uint32_t)((jc + 2) * 32), ra);
-        process(rb, jc);
-        tmem_ld_wait();
-        jc += 2;
+        if (h == nhalf - 1) {   // every TMEM load of this thread has landed: the MMA warp may overwrite the accumulators
+          tc_fence_before();
+          mbar_arrive(bar_tempty);
+        }
+        if (!p.up2) {
+          fence_proxy_async_smem();           // staging rows written through the generic proxy -> visible to the TMA engine
+          named_bar_sync(1 + q, 64);
+          const int npx = min(CONV_HALF, wi.G * CONV_TM - CONV_HALF * h);
+          if (issuer && nchunk > 0 && !(p.dbg & 2)) {
+            bulk_s2g(out_pl + (long long)lane * og.PL * 8 + (long long)(p.lead + wi.m0 + CONV_HALF * h) * 8,
+                     stg_q + (uint32_t)(lane * CONV_SPLANE), (uint32_t)npx * 16u);
+            bulk_commit();
+          }
+        }
       }
-      if (!do_stats) { ssum = 0.f; ssq = 0.f; }
-      // accumulators are drained: the MMA warp may reuse this TMEM stage
-      tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * acc);
 
-      if (do_stats) {  // quad (4-channel) partial sums: combine 4 neighbouring lanes, fp64 atomics
-        ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
-        ssq += __shfl_xor_sync(0xffffffffu, ssq, 1);
-        ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
-        ssq += __shfl_xor_sync(0xffffffffu, ssq, 2);
-        if ((lane & 3) == 0) {
+      if (do_stats) {  // quad (4-channel) partial sums: channels 4k..4k+3 of a plane sit in lanes 4 apart; fp64 atomics
+        const float2 s2 = f2_unpack(ssum2), q2 = f2_unpack(ssq2);
+        float ssum = s2.x + s2.y, ssq = q2.x + q2.y;
+        ssum += __shfl_xor_sync(0xffffffffu, ssum, 4);
+        ssq += __shfl_xor_sync(0xffffffffu, ssq, 4);
+        ssum += __shfl_xor_sync(0xffffffffu, ssum, 8);
+        ssq += __shfl_xor_sync(0xffffffffu, ssq, 8);
+        if ((lane & 12) == 0) {
           stat_t* sdst = p.stats + ((long long)wi.n * (p.cout >> 2) + (c >> 2)) * 2;
           atomicAdd(sdst, (stat_t)ssum);
           atomicAdd(sdst + 1, (stat_t)ssq);
         }
       }
     }
+    if (issuer) bulk_wait_all();   // shared memory must outlive the engine's reads; the stores complete before the CTA exits
   } else {
-    // ================================ transform warps (2, 8..11): GroupNorm(+SiLU) of the landed windows, in place
-    const int tt = ((warp == 2) ? 0 : (warp - 7)) * 32 + lane;  // 0..159
+    // ================================ transform warps (2, 8..11): GroupNorm(+SiLU) of the landed windows, in place.
+    // Every 256-pixel sweep is split into 8 groups of 32 pixels: warps 8, 9, 11 (alone on their sub-partition among the
+    // transform warps) take two groups, warps 2 and 10 (same sub-partition) one each.
+#ifndef CONV_XF_BALANCED   // equal shares (five warps x 1.6 groups does not divide: use 5 of 8 groups per 160-px sweep)
+    const int xg0 = (warp == 2) ? 0 : (warp - 7);
+    const int xng = 1;
+    constexpr int XSWEEP = 160;
+#else
+    const int xg0 = (warp == 8) ? 0 : (warp == 9) ? 2 : (warp == 11) ? 4 : (warp == 2) ? 6 : 7;
+    const int xng = (warp == 2 || warp == 10) ? 1 : 2;
+    constexpr int XSWEEP = 256;
+#endif
     int stage = 0;
     uint32_t phase = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
@@ -343,41 +403,53 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
         const ConvSeg& sg = p.seg[s];
         const int npix = wi.G * CONV_TM + (sg.ht + sg.hb) * p.Wp + sg.hl + sg.hr;
         const float2* ssn = sg.ss ? sg.ss + (long long)wi.n * sg.ss_stride : nullptr;
-        // flat position of this thread's first pixel; (row, col) advance incrementally (CONV_XF_THREADS pixels per step)
-        const int m_first = wi.m0 - sg.ht * p.Wp - sg.hl + tt;
-        const int row0 = (m_first >= 0) ? m_first / p.Wp : -1 - ((-1 - m_first) / p.Wp);  // floor division
-        const int col0 = m_first - row0 * p.Wp;
-        const int drow = CONV_XF_THREADS / p.Wp, dcol = CONV_XF_THREADS - drow * p.Wp;
+        // flat position of this thread's first pixel(s); (row, col) advance incrementally (256 pixels per sweep)
+        int row0[2], col0[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int m_first = wi.m0 - sg.ht * p.Wp - sg.hl + (xg0 + u) * 32 + lane;
+          row0[u] = (m_first >= 0) ? m_first / p.Wp : -1 - ((-1 - m_first) / p.Wp);  // floor division
+          col0[u] = m_first - row0[u] * p.Wp;
+        }
+        const int drow = XSWEEP / p.Wp, dcol = XSWEEP - drow * p.Wp;
         const bool silu = sg.silu != 0;
         for (int ks = 0; ks < sg.ksteps; ++ks) {
-          float2 ss0[8], ss1[8];
+          f32x2_t sc0[4], sh0[4], sc1[4], sh1[4];
           if (ssn) {
             const float4* sp = reinterpret_cast<const float4*>(ssn + ks * 16);
             const float hs = silu ? 0.5f : 1.0f;  // SiLU path works on a/2 (see xform_vec)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float4 a = __ldg(sp + e), b = __ldg(sp + 4 + e);
-              ss0[2 * e] = make_float2(a.x * hs, a.y * hs); ss0[2 * e + 1] = make_float2(a.z * hs, a.w * hs);
-              ss1[2 * e] = make_float2(b.x * hs, b.y * hs); ss1[2 * e + 1] = make_float2(b.z * hs, b.w * hs);
+              const float4 a = __ldg(sp + e), b = __ldg(sp + 4 + e);   // (scale, shift) of channels 2e, 2e+1 | 8+2e, 9+2e
+              sc0[e] = f2_pack(a.x * hs, a.z * hs); sh0[e] = f2_pack(a.y * hs, a.w * hs);
+              sc1[e] = f2_pack(b.x * hs, b.z * hs); sh1[e] = f2_pack(b.y * hs, b.w * hs);
             }
           }
           mbar_wait(bar_fullA + 8 * stage, phase);
           if (ssn && !(p.dbg & 64)) {
             uint4* base = reinterpret_cast<uint4*>(smem + stage * a_bytes);
-            int row = row0, col = col0;
-            for (int px = tt; px < npix; px += CONV_XF_THREADS) {
-              const bool valid = (row >= 0) && (row < p.H) && (col < p.W);
-              uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
-              if (valid) {
-                a = base[px];
-                b = base[npix + px];
-                if (silu) { a = xform_vec<true>(a, ss0); b = xform_vec<true>(b, ss1); }
-                else      { a = xform_vec<false>(a, ss0); b = xform_vec<false>(b, ss1); }
+            int row[2] = {row0[0], row0[1]}, col[2] = {col0[0], col0[1]};
+            for (int px0 = xg0 * 32 + lane; px0 < npix; px0 += XSWEEP) {
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                if (u < xng) {
+                  const int px = px0 + u * 32;
+                  if (px < npix) {
+                    const bool valid = (row[u] >= 0) && (row[u] < p.H) && (col[u] < p.W);
+                    uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+                    if (valid) {
+                      a = base[px];
+                      b = base[npix + px];
+                      if (silu) { a = xform_vec<true>(a, sc0, sh0); b = xform_vec<true>(b, sc1, sh1); }
+                      else      { a = xform_vec<false>(a, sc0, sh0); b = xform_vec<false>(b, sc1, sh1); }
+                    }
+                    base[px] = a;
+                    base[npix + px] = b;
+                  }
+                  row[u] += drow; col[u] += dcol;
+                  if (col[u] >= p.Wp) { col[u] -= p.Wp; ++row[u]; }
+                }
               }
-              base[px] = a;
-              base[npix + px] = b;
-              row += drow; col += dcol;
-              if (col >= p.Wp) { col -= p.Wp; ++row; }
             }
             fence_proxy_async_smem();
           }
@@ -393,51 +465,44 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-template <int CFG>
-static cudaError_t launch_cfg(const ConvParams& p, int grid, size_t smem, cudaStream_t stream) {
-  constexpr ConvCfg c = CONV_CFGS[CFG];
-  auto kern = conv_tc_kernel<c.maxg, c.acc, c.astages, c.bstages>;
-  static size_t attr = 0;
-  if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr = smem;
-  }
-  kern<<<grid, CONV_THREADS, smem, stream>>>(p);
-  return cudaGetLastError();
-}
-
 cudaError_t launch_conv_tc(const ConvParams& p_in, int num_sms, cudaStream_t stream) {
-  static int dbg = -1, cfg_env = -1;
+  static int dbg = -1;
   if (dbg < 0) {
     const char* e = getenv("B200AD_CONV_DBG");
     dbg = e ? atoi(e) : 0;
-    const char* c = getenv("B200AD_CONV_CFG");
-    cfg_env = c ? atoi(c) : 0;
-    if (cfg_env < 0 || cfg_env > 1) cfg_env = 0;
   }
+  if (p_in.nseg < 1 || p_in.nseg > CONV_MAXSEG) return cudaErrorInvalidValue;
   ConvParams p = p_in;
   p.dbg = dbg;
-  const ConvCfg cfg = CONV_CFGS[cfg_env];
-  p.maxg = cfg.maxg;
-  p.groups_per_img = (p.H * p.Wp + cfg.maxg * CONV_TM - 1) / (cfg.maxg * CONV_TM);
+  for (int s = 0; s < p.nseg; ++s)
+    if (p.seg[s].wtile_stride == 0) p.seg[s].wtile_stride = (long long)p.seg[s].ksteps * p.seg[s].ntaps * (CONV_B_TAP / 2);
+  p.ktotal = 0;
+  for (int s = 0; s < p.nseg; ++s) p.ktotal += p.seg[s].ksteps;
+  p.groups_per_img = (p.H * p.Wp + CONV_MAXG * CONV_TM - 1) / (CONV_MAXG * CONV_TM);
   p.ntiles_n = p.cout / CONV_NT;
   p.total_work = p.N * p.groups_per_img * p.ntiles_n;
   // the two windows of one k-step must fit an activation slot
   int a_stage = 0;
   for (int s = 0; s < p.nseg; ++s) {
     const ConvSeg& sg = p.seg[s];
-    const int npix = cfg.maxg * CONV_TM + (sg.ht + sg.hb) * p.Wp + sg.hl + sg.hr;
+    const int npix = CONV_MAXG * CONV_TM + (sg.ht + sg.hb) * p.Wp + sg.hl + sg.hr;
     a_stage = npix * 32 > a_stage ? npix * 32 : a_stage;
-    if (sg.ntaps > CONV_MAXTAPS || npix > 0x3FFF) return cudaErrorInvalidValue;
+    if (sg.ntaps > CONV_MAXTAPS || sg.ntaps > CONV_BT * (CONV_BS - 1) || npix > 0x3FFF) return cudaErrorInvalidValue;
     for (int t = 0; t < sg.ntaps; ++t) p.seg[s].aoff[t] = (sg.dh[t] + sg.ht) * p.Wp + sg.dw[t] + sg.hl;
   }
   p.a_stage = (a_stage + 255) & ~255;
-  const size_t smem = (size_t)cfg.astages * p.a_stage + (size_t)cfg.bstages * CONV_B_SLOT + 8 * CONV_TTILE + 1024;
+  const size_t smem = (size_t)CONV_AS * p.a_stage + (size_t)CONV_BS * CONV_B_SLOT + CONV_STAGING + 1024;
   if (smem > (size_t)CONV_SMEM_MAX) return cudaErrorInvalidValue;  // image too wide for this tiling
   const int grid = p.total_work < num_sms ? p.total_work : num_sms;
   if (grid <= 0) return cudaSuccess;
-  return cfg_env == 0 ? launch_cfg<0>(p, grid, smem, stream) : launch_cfg<1>(p, grid, smem, stream);
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr = smem;
+  }
+  conv_tc_kernel<<<grid, CONV_THREADS, smem, stream>>>(p);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------ identity weights
@@ -448,7 +513,7 @@ __global__ void pack_identity_kernel(int channels, __nv_bfloat16* __restrict__ d
   const long long rest = id >> 8;
   const int ksteps = channels / 16;
   const int ks = (int)(rest % ksteps), ntile = (int)(rest / ksteps);
-  const int co = ntile * 128 + n8 * 8 + r;
+  const int co = ntile * 128 + conv_lane_channel(n8 * 8 + r);
   const int ci0 = ks * 16 + k8 * 8;
   uint32_t o[4];
 #pragma unroll

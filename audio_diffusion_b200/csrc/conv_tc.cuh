@@ -4,32 +4,30 @@
 
 namespace b200ad {
 
-constexpr int CONV_NT = 128;        // output-channel tile = MMA N
-constexpr int CONV_TM = 128;        // pixels per MMA tile = MMA M
-constexpr int CONV_MAXSEG = 4;
+constexpr int CONV_NT = 128;        // output-channel tile = MMA M (TMEM lanes)
+constexpr int CONV_TM = 128;        // pixels per tile; an MMA covers up to two tiles (N = 256)
+constexpr int CONV_MAXG = 4;        // pixel tiles per work item: 4 x 128 fp32 columns = all of TMEM
+constexpr int CONV_MAXSEG = 6;      // K-segments per launch (callers use up to 4; the launcher may split one, see below)
 constexpr int CONV_MAXTAPS = 9;
 constexpr int CONV_B_TAP = 16 * CONV_NT * 2;     // one tap, 16 input channels: 4096 B
-constexpr int CONV_B_STAGE = CONV_MAXTAPS * CONV_B_TAP;
 constexpr int CONV_SMEM_MAX = 227 * 1024;
 
-// Kernel configurations (compile-time): pixel tiles per work item, TMEM accumulator stages, smem ring depth.
-//   cfg 0: 4 tiles, 1 accumulator stage  (4 x 128 columns = all of TMEM; weights reused by 4 tiles; epilogue exposed)
-//   cfg 1: 2 tiles, 2 accumulator stages (epilogue of item k overlaps the MMAs of item k+1; twice the weight traffic)
-// Shared memory holds two independent rings: `astages` activation slots (one 16-channel k-step each: two 8-channel
-// windows) and `bstages` weight slots of CONV_BT taps each, so weights (the bulk of the bytes) are prefetched at a finer
+// Shared memory holds two independent rings: CONV_AS activation slots (one 16-channel k-step each: two 8-channel
+// windows) and CONV_BS weight slots of CONV_BT taps each, so weights (the bulk of the bytes) are prefetched at a finer
 // grain and the TMA -> transform -> MMA chain of the activations gets a deeper ring.
-struct ConvCfg { int maxg, acc, astages, bstages; };
 constexpr int CONV_BT = 3;                       // taps per weight slot
 constexpr int CONV_B_SLOT = CONV_BT * CONV_B_TAP;
-constexpr ConvCfg CONV_CFGS[2] = {{4, 1, 4, 6}, {2, 2, 4, 8}};
+constexpr int CONV_AS = 3;   // (4 / 6 measured the same as 3 / 5 in round 1; the bytes now buy the epilogue staging buffer)
+constexpr int CONV_BS = 5;
 
 // One K-segment: a source tensor (PF8) with its tap set and packed weights. A 3x3 conv is one
 // segment with 9 taps; a fused 1x1 shortcut adds one 1-tap segment per shortcut source; a stride-2
 // conv is four segments (one per input parity plane).
 struct ConvSeg {
   const __nv_bfloat16* src;    // PF8 activations, same geometry as the output
-  const __nv_bfloat16* wpack;  // [cout/128][ksteps][ntaps][2 k8][16 n8][8][8] bf16
+  const __nv_bfloat16* wpack;  // [cout/128][ksteps][ntaps][2 k8][16 lanes8][8][8] bf16, rows in conv_lane_channel order
   long long img_stride;        // elements between images of src (= C/8 * PL * 8)
+  long long wtile_stride;      // elements between cout tiles of wpack (0: ksteps * ntaps * 2048; set by the launcher)
   int ksteps;                  // input channels / 16
   int ntaps;
   int ht, hb, hl, hr;          // halo rows above / below, pixels left / right
@@ -47,7 +45,7 @@ struct ConvParams {
   ConvSeg seg[CONV_MAXSEG];
   int nseg;
   int N, H, W, Wp, lead, PL;
-  int maxg;             // pixel tiles per work item (set by the launcher from the chosen configuration)
+  int ktotal;           // sum of the segments' k-steps (set by the launcher)
   int a_stage;          // bytes reserved for the A strips of one stage (set by the launcher)
   int groups_per_img;
   int ntiles_n;         // cout / 128
@@ -61,7 +59,7 @@ struct ConvParams {
   // Folded nearest-2x upsample: the item geometry (N, H, W, ...) is the LOW-res input; low-res pixel (h, w) is stored at
   // (2h + oy, 2w + ox) of the (2H, 2W) output tensor. One launch per output parity (oy, ox) with pre-summed 2x2 weights.
   int up2, oy, ox;
-  int dbg;                      // B200AD_CONV_DBG bit flags (timing experiments only): 1 no stats, 2 no stores, 4 no tmem ld, 8 no epilogue
+  int dbg;                      // B200AD_CONV_DBG bit flags (timing experiments only): 8 no epilogue work, 16 no skew, 64 no transform
 };
 
 cudaError_t launch_conv_tc(const ConvParams& p, int num_sms, cudaStream_t stream);

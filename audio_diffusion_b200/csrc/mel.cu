@@ -137,13 +137,13 @@ __global__ void __launch_bounds__(256) dec_pinv_kernel(const uint8_t* __restrict
     for (int i = threadIdx.x; i < 16 * 64; i += 256) {
       const int kk = i & 15, ff = i >> 4;  // pinv is [F][M]: consecutive threads read consecutive m
       const int f = f0 + ff;
-      sp[kk][ff] = (f < d.F) ? pinv[(size_t)f * d.M + k0 + kk] : 0.0;
+      sp[kk][ff] = (f < d.F && k0 + kk < d.M) ? pinv[(size_t)f * d.M + k0 + kk] : 0.0;   // y_res need not be a multiple of 16
     }
     for (int i = threadIdx.x; i < 16 * 64; i += 256) {
       const int tt = i & 63, kk = i >> 6;  // image is [M][T]: consecutive threads read consecutive t
       const int t = t0 + tt;
       double v = 0.0;
-      if (t < d.T) {
+      if (t < d.T && k0 + kk < d.M) {
         const double bb = (double)img[((size_t)n * d.M + k0 + kk) * d.T + t];
         const double ldb = bb * top_db / 255.0 - top_db;  // mel.py:163
         v = pow(10.0, 0.1 * ldb);                          // librosa.db_to_power

@@ -118,6 +118,13 @@ static PackItem make_pack_item(const NetBase* h, const PackJob& j, uint8_t* aren
   return it;
 }
 
+static const char* check_groups(const int* ch, int n, int groups) {
+  if (groups < 1 || groups > 64) return "norm_num_groups must be in 1..64";
+  for (int i = 0; i < n; ++i)   // GroupNorm partial sums are kept per 4-channel quad: a group must be whole quads
+    if (ch[i] % groups || (ch[i] / groups) % 4) return "channels per GroupNorm group must be a multiple of 4 for every block";
+  return nullptr;
+}
+
 static void add_param(NetBase* h, const std::string& name, std::vector<int64_t> shape) {
   h->pidx[name] = (int)h->params.size();
   h->params.push_back({name, std::move(shape)});

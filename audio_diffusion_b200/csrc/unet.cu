@@ -130,6 +130,7 @@ extern "C" int b200ad_unet_create(const b200ad_unet_config* cfg, b200ad_unet** o
   for (int i = 0; i < cfg->num_blocks; ++i)
     if (cfg->block_out_channels[i] % 128) return set_err("block_out_channels must be multiples of 128");
   if (cfg->out_channels > 4) return set_err("out_channels > 4 not implemented");
+  if (const char* e = check_groups(cfg->block_out_channels, cfg->num_blocks, cfg->norm_num_groups)) return set_err("%s", e);
   b200ad_unet* h = new b200ad_unet();
   h->cfg = *cfg;
   h->norm_groups = cfg->norm_num_groups;
@@ -476,8 +477,14 @@ extern "C" int b200ad_unet_profile_step(b200ad_unet* h, const float* x, const fl
     if (saved[i].kind == OP_CONV) {
       const ConvParams& p = saved[i].conv;
       double k = 0;
-      // algorithmic taps: a folded upsample launch stands for the 3x3 conv on its quarter of the output pixels
-      for (int s = 0; s < p.nseg; ++s) k += (double)(p.up2 ? 9 : p.seg[s].ntaps) * p.seg[s].ksteps * 16;
+      // algorithmic taps: a folded upsample launch stands for the 3x3 conv on its quarter of the output pixels; a residual
+      // add carried as an identity-weight K-segment is an addition, not a convolution: no algorithmic FLOPs
+      for (int s = 0; s < p.nseg; ++s) {
+        bool ident = false;
+        for (const auto& kv : h->ident_off)
+          if ((const uint8_t*)p.seg[s].wpack == h->packed + kv.second) ident = true;
+        if (!ident) k += (double)(p.up2 ? 9 : p.seg[s].ntaps) * p.seg[s].ksteps * 16;
+      }
       fl = 2.0 * p.N * p.H * p.W * p.cout * k;
     }
     op_flops[i] = fl;

@@ -367,6 +367,7 @@ extern "C" int b200ad_vae_create(const b200ad_vae_config* cfg, b200ad_vae** out)
     if (cfg->block_out_channels[i] % 128) return set_err("block_out_channels must be multiples of 128");
   if (cfg->latent_channels < 1 || cfg->latent_channels > 4) return set_err("latent_channels must be 1..4");
   if (cfg->out_channels > 4) return set_err("out_channels > 4 not implemented");
+  if (const char* e = check_groups(cfg->block_out_channels, cfg->num_blocks, cfg->norm_num_groups)) return set_err("%s", e);
   b200ad_vae* h = new b200ad_vae();
   h->cfg = *cfg;
   h->norm_groups = cfg->norm_num_groups;

@@ -192,6 +192,16 @@ class DDIMScheduler(_SchedulerBase):
     def needs_noise(self, timestep, eta: float = 0.0) -> bool:
         return eta > 0
 
+    def invert_step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor) -> torch.Tensor:
+        """One step of deterministic DDIM inversion, x_{t-Δ} -> x_t (audiodiffusion/pipeline_audio_diffusion.py:229-240):
+        remove the ε-direction at the lower noise level, rescale to x0, then re-noise to level t with the same ε."""
+        t = int(timestep)
+        prev_t = t - self.config.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
+        x0 = (sample - (1 - a_prev) ** 0.5 * model_output) * a_prev ** (-0.5)
+        return x0 * a_t ** 0.5 + (1 - a_t) ** 0.5 * model_output
+
     def step_coef(self, timestep, eta: float = 0.0) -> StepCoefC:
         t = int(timestep)
         a_t, a_prev, b_t, std = self._scalars(t, eta)

@@ -1,11 +1,12 @@
-"""Optimizer side of `scripts/train_unet.py`'s training step on the B200 engine (partial).
+"""Optimizer side of `scripts/train_unet.py`'s training step on the B200 engine.
 
 `FusedAdamW` has the `torch.optim.AdamW` constructor the reference uses (train_unet.py:166-172) and folds
 `accelerator.clip_grad_norm_(model.parameters(), 1.0)` (:262), the AdamW update (:263) and `EMAModel.step` (:265-266)
 into one pass over all parameters (`b200ad_optim_step`, two launches).  `EMAModel` keeps diffusers==0.24's surface
 (`step`, `copy_to`, `decay`, `get_decay`).  `mse_loss` is `F.mse_loss` + dL/dpred in one kernel.
 
-The U-Net backward is not built yet: gradients have to come from elsewhere (tests use synthetic ones).
+`train_step` is the loop body of train_unet.py:238-267 on the engine (forward and backward in libb200ad.so through
+`UNet2DModel`'s autograd node); the unchanged reference script itself runs on `compat/accelerate`.
 """
 from __future__ import annotations
 
@@ -99,8 +100,9 @@ class FusedAdamW(torch.optim.Optimizer):
             raise ValueError("FusedAdamW supports a single parameter group")
         self.max_grad_norm = max_grad_norm
         self._h = None
+        self._bound_key = None
         self._ema: Optional[EMAModel] = None
-        self._steps = 0
+        self.param_groups[0].setdefault("step", 0)     # lives in the param group so state_dict() / resume keeps it
         self.grad_norm: Optional[torch.Tensor] = None
 
     def attach_ema(self, ema: EMAModel) -> None:
@@ -112,6 +114,26 @@ class FusedAdamW(torch.optim.Optimizer):
         if self._h is not None:
             _lib.lib().b200ad_optim_destroy(self._h)
             self._h = None
+        self._bound_key = None
+
+    def load_state_dict(self, state_dict):
+        """Resume: the moments are replaced by the loaded tensors, so the raw pointers held by the kernel handle are stale."""
+        super().load_state_dict(state_dict)
+        self.param_groups[0].setdefault("step", 0)
+        self._release()
+
+    def _pointer_key(self):
+        """Every device pointer the kernel handle holds: parameters, both moments and (if attached) the EMA shadows."""
+        g = self.param_groups[0]["params"]
+        key = []
+        for i, p in enumerate(g):
+            if not p.requires_grad:
+                continue
+            st = self.state.get(p, {})
+            key.append((p.data_ptr(), st["exp_avg"].data_ptr() if "exp_avg" in st else 0,
+                        st["exp_avg_sq"].data_ptr() if "exp_avg_sq" in st else 0,
+                        self._ema.shadow_params[i].data_ptr() if self._ema is not None else 0))
+        return tuple(key)
 
     def __del__(self):
         try:
@@ -146,10 +168,14 @@ class FusedAdamW(torch.optim.Optimizer):
             _lib.check(_lib.lib().b200ad_optim_create(n, sizes, arr(ps), arr([self.state[p]["exp_avg"] for p in ps]),
                                                       arr([self.state[p]["exp_avg_sq"] for p in ps]), ema, C.byref(h)))
         self._h = h
+        self._bound_key = self._pointer_key()
 
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
+        # module.to(), optimizer.load_state_dict() and EMAModel.to() all replace tensors: rebind when any pointer moved
+        if self._h is not None and self._pointer_key() != self._bound_key:
+            self._release()
         if self._h is None:
             self._bind()
         g = self.param_groups[0]
@@ -162,10 +188,10 @@ class FusedAdamW(torch.optim.Optimizer):
             if gr.dtype != torch.float32 or not gr.is_contiguous():
                 gr = gr.to(torch.float32).contiguous()
             grads.append(gr)
-        self._steps += 1
+        g["step"] = int(g.get("step", 0)) + 1
         hp = OptimHParamsC(g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"],
                            self.max_grad_norm if self.max_grad_norm else -1.0,
-                           self._ema.next_decay() if self._ema is not None else -1.0, self._steps)
+                           self._ema.next_decay() if self._ema is not None else -1.0, g["step"])
         if self.grad_norm is None:
             self.grad_norm = torch.zeros(1, dtype=torch.float32, device=ps[0].device)
         arr = (C.c_void_p * len(grads))(*[t.data_ptr() for t in grads])

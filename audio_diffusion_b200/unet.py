@@ -81,10 +81,25 @@ class UNet2DModel(nn.Module):
         norm_eps: float = 1e-5,
         resnet_time_scale_shift: str = "default",
         add_attention: bool = True,
+        downsample_type: str = "conv",
+        upsample_type: str = "conv",
+        dropout: float = 0.0,
+        attn_norm_num_groups: Optional[int] = None,
+        class_embed_type: Optional[str] = None,
+        num_class_embeds: Optional[int] = None,
+        num_train_timesteps: Optional[int] = None,
         seed: Optional[int] = None,
     ):
         super().__init__()
         unsupported = []
+        if downsample_type != "conv" or upsample_type != "conv": unsupported.append("downsample_type/upsample_type")
+        if dropout: unsupported.append("dropout")
+        if attn_norm_num_groups is not None and attn_norm_num_groups != norm_num_groups: unsupported.append("attn_norm_num_groups")
+        if class_embed_type is not None or num_class_embeds is not None: unsupported.append("class embedding")
+        for ch in block_out_channels:     # GroupNorm statistics are accumulated per 4-channel quad (csrc/conv_tc.cu)
+            if ch % norm_num_groups or (ch // norm_num_groups) % 4:
+                unsupported.append(f"norm_num_groups={norm_num_groups} with {ch} channels (channels per group must be a multiple of 4)")
+                break
         if center_input_sample: unsupported.append("center_input_sample")
         if time_embedding_type != "positional": unsupported.append("time_embedding_type")
         if freq_shift != 0 or not flip_sin_to_cos: unsupported.append("freq_shift/flip_sin_to_cos")
@@ -108,7 +123,9 @@ class UNet2DModel(nn.Module):
             center_input_sample=center_input_sample, time_embedding_type=time_embedding_type, freq_shift=freq_shift,
             flip_sin_to_cos=flip_sin_to_cos, mid_block_scale_factor=mid_block_scale_factor,
             downsample_padding=downsample_padding, act_fn=act_fn, resnet_time_scale_shift=resnet_time_scale_shift,
-            add_attention=add_attention, _class_name="UNet2DModel")
+            add_attention=add_attention, downsample_type=downsample_type, upsample_type=upsample_type, dropout=dropout,
+            attn_norm_num_groups=attn_norm_num_groups, class_embed_type=class_embed_type,
+            num_class_embeds=num_class_embeds, num_train_timesteps=num_train_timesteps, _class_name="UNet2DModel")
 
         c = UNetConfigC()
         c.in_channels, c.out_channels = in_channels, out_channels
@@ -148,6 +165,19 @@ class UNet2DModel(nn.Module):
         self._packed_key = None
         self._ws = None
         self._ws_key = None
+
+    # ------------------------------------------------------------------ diffusers ModelMixin persistence
+    @classmethod
+    def from_pretrained(cls, path: str, subfolder: Optional[str] = None, **_unused) -> "UNet2DModel":
+        """`<path>/config.json` + `diffusion_pytorch_model.{safetensors,bin}`; older hub files' attention key names
+        (query/key/value/proj_attn) are renamed on the way in."""
+        import os
+        from .hub_io import model_from_dir
+        return model_from_dir(cls, os.path.join(path, subfolder) if subfolder else path)
+
+    def save_pretrained(self, path: str, safe_serialization: bool = True, **_unused) -> None:
+        from .hub_io import save_model
+        save_model(self, path, safe_serialization=safe_serialization)
 
     # ------------------------------------------------------------------ engine plumbing
     def __del__(self):

@@ -166,6 +166,33 @@ def test_mel_nnls_is_initial_point_on_image_domain():
     assert d["nit"] == 0 and np.array_equal(x.reshape(x0.shape), x0)
 
 
+@pytest.mark.parametrize("kind", ["zeros", "ones", "random", "checker", "tone"])
+def test_mel_nnls_initial_point_256x256_per_librosa_block(kind):
+    """The same pin at the benchmarked size: 256 mels x 256 frames, split into librosa's column blocks
+    (MAX_MEM_BLOCK 2**18 bytes / (256 mels * 8 B) = 128 columns), on degenerate and arbitrary byte images.
+    L-BFGS-B returns at iteration 0 with x == clip(pinv(A) @ S, 0) for every block: the objective carries a 1/size
+    factor, so on the image domain (S <= 1) the projected-gradient test (pgtol 1e-5) passes at the initial point."""
+    import scipy.optimize
+    from oracle import mel_oracle as mo
+    rng = np.random.default_rng(0)
+    b = {"zeros": lambda: np.zeros((256, 256), np.uint8), "ones": lambda: np.full((256, 256), 255, np.uint8),
+         "random": lambda: rng.integers(0, 256, (256, 256), dtype=np.uint8),
+         "checker": lambda: ((np.indices((256, 256)).sum(0) % 2) * 255).astype(np.uint8),
+         "tone": lambda: mo.audio_slice_to_bytes(_tone(noise=0.2, seed=5), n_mels=256)}[kind]()
+    S = mo.u8_to_power(b)
+    A = mo.mel_filterbank(22050, 2048, 256, dtype=S.dtype)
+    pinv = np.linalg.pinv(A)
+    ncol = int((2 ** 8 * 2 ** 10) // (256 * A.itemsize))
+    assert ncol == 128
+    for s0 in range(0, 256, ncol):
+        B = S[:, s0:s0 + ncol]
+        x0 = np.clip(pinv @ B, 0, None)
+        x, f, d = scipy.optimize.fmin_l_bfgs_b(mo._nnls_obj, x0, args=(x0.shape, A, B), bounds=[(0, None)] * x0.size)
+        assert d["nit"] == 0 and d["funcalls"] == 1 and np.array_equal(x.reshape(x0.shape), x0), (kind, s0, d)
+    # and the oracle's own nnls (which runs the optimiser) returns exactly that closed form
+    assert np.array_equal(mo.nnls(A, S), np.clip(pinv @ S, 0, None))
+
+
 def test_mel_roundtrip_in_mel_domain():
     from oracle import mel_oracle as mo
     cfg = dict(sr=22050, n_fft=2048, hop=512)

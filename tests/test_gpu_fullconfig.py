@@ -1,0 +1,208 @@
+"""GPU parity at the BENCHMARKED configuration: the full scripts/train_unet.py:115-137
+architecture at 256x256 per layer, free-running DDIM-50 / DDPM-100 trajectories of the full architecture at 64x64 with a
+stated drift tolerance on the final uint8 image, and the audio-conditioned / in-painting branch of the fused loop
+(audiodiffusion/pipeline_audio_diffusion.py:134-157,181-185) against the same loop on the CPU oracle.
+
+Stated tolerances (bf16 activations + bf16 GEMM operands with fp32 accumulation vs the fp32 oracle):
+  * epsilon at 256x256: max|err| <= 6 % of the tensor's max-abs, rms error <= 1.5 % of its rms (same bar as the
+    small-resolution tests); per layer: max <= 6 %, rms <= 2.5 % - every bf16 store adds ~0.3 % rms and the error
+    accumulates along the residual chain (measured 0.2 % at conv_in -> 1.5 % after the 26 layers of the down path);
+  * full trajectory, final uint8 image (random-init weights - NOT a contractive denoiser):
+      DDPM-100 (64x64, reference architecture, shared noise stream): mean |Δ| <= 1 grey level, >= 99 % of pixels within 2
+        (measured 0.10 / 100 %: the shared noise and the per-step clamp of x0 keep the two trajectories together);
+      DDIM-50 (eta 0, deterministic): with random weights the sampler map is chaotic - the ORACLE's own trajectory from an
+        initial noise merely rounded to bf16 (relative 2^-9) ends 20+ grey levels away from its unperturbed self.  The
+        bar is therefore relative: the CUDA path's drift from the oracle must not exceed 1.5 x that self-drift (+1 level);
+        (measured r2: CUDA 23.5 levels).  The teacher-forced per-step test (test_gpu_pipeline.py, rms <= 3 % per step)
+        is the absolute DDIM bar;
+    the measured values are printed (pytest -s) and recorded in DESIGN.md §4;
+  * in-painting: the columns taken from the conditioning frames are bit-identical; the generated part obeys the
+    few-step trajectory bar (>= 90 % of pixels within 2 grey levels after 6 steps).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REF_ARCH = dict(
+    in_channels=1, out_channels=1, layers_per_block=2, block_out_channels=(128, 128, 256, 256, 512, 512),
+    down_block_types=("DownBlock2D",) * 4 + ("AttnDownBlock2D", "DownBlock2D"),
+    up_block_types=("UpBlock2D", "AttnUpBlock2D", "UpBlock2D", "UpBlock2D", "UpBlock2D", "UpBlock2D"))
+SMALL = dict(
+    in_channels=1, out_channels=1, layers_per_block=2, block_out_channels=(128, 256),
+    down_block_types=("DownBlock2D", "AttnDownBlock2D"), up_block_types=("AttnUpBlock2D", "UpBlock2D"))
+
+
+def _build(cuda, arch, size, seed=0):
+    from audio_diffusion_b200.unet import UNet2DModel
+    from oracle.unet_oracle import UNetConfig, init_weights
+    ocfg = UNetConfig(sample_size=size, **arch)
+    w = init_weights(ocfg, seed=seed)
+    model = UNet2DModel(sample_size=size, **arch)
+    model.load_state_dict(w)
+    return model.to(cuda), ocfg, w
+
+
+def _rel(got, ref):
+    err = got - ref
+    mx = err.abs().max().item() / (ref.abs().max().item() + 1e-12)
+    rms = (err.pow(2).mean().sqrt() / (ref.pow(2).mean().sqrt() + 1e-12)).item()
+    return mx, rms
+
+
+def _u8(x):
+    return ((x / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1).numpy() * 255).round().astype("uint8")[..., 0]
+
+
+def test_unet_reference_arch_256_per_layer(cuda, monkeypatch):
+    """Every resnet / attention / resampler output of the reference architecture at 256x256 (the 256^2 and 128^2 levels
+    are 77 % of the FLOPs and the only ones on the W = 256 tiling with the full channel mix), batch 2, vs the fp32 oracle."""
+    from oracle.unet_oracle import unet_forward
+    monkeypatch.setenv("B200AD_DEBUG_NOPOOL", "1")
+    model, ocfg, w = _build(cuda, REF_ARCH, (256, 256))
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(2, 1, 256, 256, generator=g)
+    t = torch.tensor([37, 911])
+    taps = {}
+    with torch.no_grad():
+        ref = unet_forward(w, ocfg, x, t, taps)
+        out = model(x.to(cuda), t.to(cuda))["sample"]
+    torch.cuda.synchronize()
+    names = ["conv_in"]
+    for i in range(6):
+        names += [f"down_blocks.{i}.resnets.{j}" for j in range(2)]
+        if i == 4:
+            names += [f"down_blocks.{i}.attentions.{j}" for j in range(2)]
+        if i != 5:
+            names.append(f"down_blocks.{i}.downsamplers.0.conv")
+    names += ["mid_block.resnets.0", "mid_block.attentions.0", "mid_block.resnets.1"]
+    for i in range(6):
+        names += [f"up_blocks.{i}.resnets.{j}" for j in range(3)]
+        if i == 1:
+            names += [f"up_blocks.{i}.attentions.{j}" for j in range(3)]
+        if i != 5:
+            names.append(f"up_blocks.{i}.upsamplers.0.conv")
+    worst = (0.0, 0.0)
+    for name in names:
+        got = model.debug_tensor(name).cpu()
+        mx, rms = _rel(got, taps[name])
+        print("%-44s max-rel %.4f rms-rel %.4f" % (name, mx, rms))
+        worst = (max(worst[0], mx), max(worst[1], rms))
+    mx, rms = _rel(out.cpu(), ref)
+    print("eps max-rel %.4f rms-rel %.4f | worst layer max-rel %.4f rms-rel %.4f" % (mx, rms, worst[0], worst[1]))
+    assert worst[0] <= 6e-2 and worst[1] <= 2.5e-2
+    assert mx <= 6e-2 and rms <= 1.5e-2
+
+
+def _oracle_trajectory(w, ocfg, osch, noise, steps, gen, eta=None):
+    from oracle.unet_oracle import unet_forward
+    osch.set_timesteps(steps)
+    x = noise.clone()
+    with torch.no_grad():
+        for t in osch.timesteps:
+            eps = unet_forward(w, ocfg, x, t)
+            x = (osch.step(eps, t, x, eta=eta, generator=gen) if eta is not None
+                 else osch.step(eps, t, x, generator=gen))["prev_sample"]
+    return x
+
+
+@pytest.mark.parametrize("kind,steps", [("ddim", 50), ("ddpm", 100)])
+def test_full_trajectory_reference_arch_64(cuda, kind, steps):
+    """Free-running sampler trajectories (no teacher forcing) through `AudioDiffusionPipeline.__call__`: DDIM-50 (the
+    reference's default DDIM step count) and DDPM with 100 steps, reference architecture at 64x64 (config C1's shape),
+    batch 2; both sides draw from CPU generators with the same seed, so the noise streams are identical."""
+    from audio_diffusion_b200.mel import Mel
+    from audio_diffusion_b200.pipeline import AudioDiffusionPipeline
+    from audio_diffusion_b200.schedulers import DDIMScheduler, DDPMScheduler
+    from oracle.schedulers_oracle import OracleDDIM, OracleDDPM
+    model, ocfg, w = _build(cuda, REF_ARCH, (64, 64))
+    sch, osch = (DDIMScheduler(), OracleDDIM()) if kind == "ddim" else (DDPMScheduler(), OracleDDPM())
+    pipe = AudioDiffusionPipeline(vqvae=None, unet=model, mel=Mel(x_res=64, y_res=64, hop_length=1024), scheduler=sch)
+    pipe.set_progress_bar_config(disable=True)
+    noise = torch.randn(2, 1, 64, 64, generator=torch.Generator().manual_seed(42))
+    ref = _oracle_trajectory(w, ocfg, osch, noise, steps, torch.Generator().manual_seed(7), eta=0.0 if kind == "ddim" else None)
+    imgs = pipe(batch_size=2, steps=steps, noise=noise.to(cuda), step_generator=torch.Generator().manual_seed(7),
+                return_audio=False)
+    got = np.stack([np.asarray(im) for im in imgs]).astype(int)
+    d = np.abs(got - _u8(ref).astype(int))
+    print(f"{kind}-{steps} full trajectory: mean |d| {d.mean():.3f} grey levels, within 2: {(d <= 2).mean():.3f}, "
+          f"within 8: {(d <= 8).mean():.3f}, max {d.max()}")
+    if kind == "ddpm":
+        assert d.mean() <= 1.0 and (d <= 2).mean() >= 0.99
+    else:
+        # sensitivity of the reference trajectory itself: same oracle, initial noise rounded to bf16
+        pert = _oracle_trajectory(w, ocfg, osch, noise.to(torch.bfloat16).to(torch.float32), steps, None, eta=0.0)
+        ds = np.abs(_u8(pert).astype(int) - _u8(ref).astype(int))
+        print(f"ddim-{steps} oracle self-drift under a bf16-rounded start: mean |d| {ds.mean():.3f}, within 8: {(ds <= 8).mean():.3f}")
+        assert d.mean() <= 1.5 * ds.mean() + 1.0
+
+
+class _FrozenMel:
+    """CPU-side stand-in with the reference Mel's surface: hands back the slice image the GPU Mel produced."""
+    hop_length = 512
+
+    def __init__(self, image, x_res, sr):
+        self.image, self.x_res, self.sr = image, x_res, sr
+
+    def load_audio(self, audio_file=None, raw_audio=None):
+        pass
+
+    def audio_slice_to_image(self, slice_index):
+        return self.image
+
+    def get_sample_rate(self):
+        return self.sr
+
+
+class _OracleUNet:
+    """`unet(x, t)["sample"]` on the CPU oracle (the duck type the pipeline's unfused branch needs)."""
+
+    def __init__(self, w, ocfg, size):
+        self.w, self.ocfg, self.sample_size, self.in_channels = w, ocfg, size, 1
+
+    def __call__(self, x, t):
+        from oracle.unet_oracle import unet_forward
+        return {"sample": unet_forward(self.w, self.ocfg, x, t)}
+
+
+@pytest.mark.parametrize("kind", ["ddpm", "ddim"])
+def test_audio_conditioned_inpainting_matches_oracle_loop(cuda, kind):
+    """`pipe(raw_audio=..., start_step=2, mask_start_secs=..., mask_end_secs=...)` on the fused GPU path vs the same stages
+    (`_start_state` / `_condition` / `_denoise`, unfused branch) on the CPU with the oracle U-Net.  tests/test_cpu_dropin.py
+    proves those CPU stages bit-identical to the reference's own pipeline file, so this is the reference loop."""
+    from audio_diffusion_b200.mel import Mel
+    from audio_diffusion_b200.pipeline import AudioDiffusionPipeline
+    from audio_diffusion_b200.schedulers import DDIMScheduler, DDPMScheduler
+    model, ocfg, w = _build(cuda, SMALL, (32, 32), seed=3)
+    mel = Mel(x_res=32, y_res=32, hop_length=512)
+    rng = np.random.default_rng(1)
+    n = mel.x_res * mel.hop_length * 2
+    audio = (0.1 * rng.standard_normal(n) + 0.5 * np.sin(2 * np.pi * 440.0 * np.arange(n) / 22050)).astype(np.float32)
+    mk = (lambda: DDPMScheduler()) if kind == "ddpm" else (lambda: DDIMScheduler())
+    steps, start = 8, 2
+    kw = dict(batch_size=1, raw_audio=audio, slice=1, start_step=start, steps=steps, mask_start_secs=0.1,
+              mask_end_secs=0.2, eta=0.5 if kind == "ddim" else 0)
+    noise = torch.randn(1, 1, 32, 32, generator=torch.Generator().manual_seed(11))
+
+    pipe = AudioDiffusionPipeline(vqvae=None, unet=model, mel=mel, scheduler=mk())
+    pipe.set_progress_bar_config(disable=True)
+    imgs = pipe(noise=noise.to(cuda), step_generator=torch.Generator().manual_seed(5), return_audio=False, **kw)
+    got = np.asarray(imgs[0]).astype(int)
+
+    mel.load_audio(raw_audio=audio)
+    cpu = AudioDiffusionPipeline(vqvae=None, unet=_OracleUNet(w, ocfg, (32, 32)),
+                                 mel=_FrozenMel(mel.audio_slice_to_image(1), mel.x_res, mel.get_sample_rate()), scheduler=mk())
+    cpu.set_progress_bar_config(disable=True)
+    cpu.scheduler.set_timesteps(steps)
+    with torch.no_grad():
+        x = cpu._start_state(1, None, noise)
+        inpaint = cpu._condition(x, None, audio, 1, start, None, 0.1, 0.2)
+        x = cpu._denoise(x, start, kw["eta"], torch.Generator().manual_seed(5), None, inpaint)
+    ref = _u8(x).astype(int)[0]
+    frames, left, right = inpaint
+    assert left == 4 and right == 8                       # 32 * 22050 / 32 / 512 = 43.07 columns per second
+    assert np.array_equal(got[:, :left], ref[:, :left]) and np.array_equal(got[:, -right:], ref[:, -right:])
+    d = np.abs(got - ref)[:, left:-right]
+    print(f"in-painting {kind}: generated part mean |d| {d.mean():.3f}, within 2: {(d <= 2).mean():.3f}, max {d.max()}")
+    assert (d <= 2).mean() >= 0.90
