@@ -20,7 +20,8 @@ class UNetConfigC(C.Structure):
         ("in_channels", C.c_int), ("out_channels", C.c_int), ("layers_per_block", C.c_int), ("num_blocks", C.c_int),
         ("block_out_channels", C.c_int * MAX_BLOCKS), ("down_attn", C.c_int * MAX_BLOCKS),
         ("up_attn", C.c_int * MAX_BLOCKS), ("norm_num_groups", C.c_int), ("norm_eps", C.c_float),
-        ("attention_head_dim", C.c_int),
+        ("attention_head_dim", C.c_int), ("cross_attention_dim", C.c_int), ("down_cross", C.c_int * MAX_BLOCKS),
+        ("up_cross", C.c_int * MAX_BLOCKS),
     ]
 
 
@@ -62,6 +63,7 @@ SYMBOLS = {
     "b200ad_unet_set_params": (_I, [_VP, C.POINTER(_VP), _VP, _SZ, _VP]),
     "b200ad_unet_bind_workspace": (_I, [_VP, _VP, _SZ, _I, _I, _I, _VP]),
     "b200ad_unet_forward": (_I, [_VP, _VP, _VP, _VP, _VP]),
+    "b200ad_unet_set_encoding": (_I, [_VP, _VP, _I]),
     "b200ad_unet_forward_step": (_I, [_VP, _VP, _VP, _VP, C.POINTER(StepCoefC), _VP, _VP, _VP]),
     "b200ad_unet_profile_step": (_I, [_VP, _VP, _VP, _VP, C.POINTER(StepCoefC), _VP, C.POINTER(C.c_float),
                                       C.POINTER(_I), C.POINTER(C.c_double), _I, _VP]),

@@ -166,8 +166,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
             for (int t0 = 0; t0 < sg.ntaps; t0 += CONV_BT) {
               const uint32_t bytes = (uint32_t)min(CONV_BT, sg.ntaps - t0) * CONV_B_TAP;
               mbar_wait(bar_emptyB + 8 * stage, phase ^ 1);
-              mbar_arrive_expect_tx(bar_fullB + 8 * stage, bytes);
-              bulk_g2s(bring_base + stage * CONV_B_SLOT, src, bytes, bar_fullB + 8 * stage);
+              if (p.dbg & 32) {      // experiment: no weight traffic at all (bounds what sharing weight fetches could buy)
+                mbar_arrive(bar_fullB + 8 * stage);
+              } else {
+                mbar_arrive_expect_tx(bar_fullB + 8 * stage, bytes);
+                bulk_g2s(bring_base + stage * CONV_B_SLOT, src, bytes, bar_fullB + 8 * stage);
+              }
               src += bytes;
               if (++stage == BS) { stage = 0; phase ^= 1; }
             }
@@ -460,9 +464,48 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
     }
   }
 
+  if (p.fin.ss) __threadfence();   // this thread's statistics atomics are ordered before the CTA's arrival below
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
+
+  // ---- GroupNorm finalize of the consumer, by the last CTA to arrive (replaces a launch per GroupNorm)
+  if (p.fin.ss) {
+    __shared__ unsigned s_last;
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = (atomicAdd(p.fin.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const ConvGnFin& f = p.fin;
+      const int Ct = f.C[0] + f.C[1], cpg = Ct / f.groups;
+      float* gmean = reinterpret_cast<float*>(smem);        // the rings are idle now: [N * groups] mean, then rstd
+      float* grstd = gmean + p.N * f.groups;
+      const double cnt = (double)cpg * (double)f.HW;
+      for (int i = threadIdx.x; i < p.N * f.groups; i += CONV_THREADS) {
+        const int n = i / f.groups, gi = i - n * f.groups;
+        double sm = 0., sq = 0.;
+        for (int c = gi * cpg; c < (gi + 1) * cpg; c += 4) {
+          const stat_t* st = (c < f.C[0]) ? f.stats[0] + ((long long)n * (f.C[0] >> 2) + (c >> 2)) * 2
+                                          : f.stats[1] + ((long long)n * (f.C[1] >> 2) + ((c - f.C[0]) >> 2)) * 2;
+          sm += __ldcg(st);
+          sq += __ldcg(st + 1);
+        }
+        const double mean = sm / cnt;
+        gmean[i] = (float)mean;
+        grstd[i] = (float)(1.0 / sqrt(fmax(sq / cnt - mean * mean, 0.) + (double)f.eps));
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < p.N * Ct; i += CONV_THREADS) {
+        const int n = i / Ct, c = i - n * Ct, gi = n * f.groups + c / cpg;
+        const float sc = __ldg(f.gamma + c) * grstd[gi];
+        f.ss[i] = make_float2(sc, __ldg(f.beta + c) - gmean[gi] * sc);
+      }
+      if (threadIdx.x == 0) *f.counter = 0u;
+    }
+  }
 }
 
 cudaError_t launch_conv_tc(const ConvParams& p_in, int num_sms, cudaStream_t stream) {

@@ -41,6 +41,20 @@ struct ConvSeg {
   int silu;
 };
 
+// GroupNorm statistics -> per-(sample, channel) (scale, shift) of the NEXT GroupNorm, computed by the last CTA of the
+// launch that completes the statistics (no separate launch): `ss[n][c] = (gamma[c] * rstd, beta[c] - mean * gamma[c] * rstd)`
+// over the channel concatenation of up to two tensors (the second one, a skip connection, was finished long before).
+struct ConvGnFin {
+  const stat_t* stats[2];   // [N][C_i / 4][2] quad (sum, sumsq)
+  int C[2];
+  const float* gamma;       // [C0 + C1]
+  const float* beta;
+  float2* ss;               // [N][C0 + C1]; nullptr: this launch finalises nothing
+  unsigned* counter;        // CTA arrival counter (zero before and after every launch)
+  int groups, HW;
+  float eps;
+};
+
 struct ConvParams {
   ConvSeg seg[CONV_MAXSEG];
   int nseg;
@@ -59,7 +73,8 @@ struct ConvParams {
   // Folded nearest-2x upsample: the item geometry (N, H, W, ...) is the LOW-res input; low-res pixel (h, w) is stored at
   // (2h + oy, 2w + ox) of the (2H, 2W) output tensor. One launch per output parity (oy, ox) with pre-summed 2x2 weights.
   int up2, oy, ox;
-  int dbg;                      // B200AD_CONV_DBG bit flags (timing experiments only): 8 no epilogue work, 16 no skew, 64 no transform
+  ConvGnFin fin;
+  int dbg;                      // B200AD_CONV_DBG bit flags (timing experiments only): 2 no stores, 4 CTAs out of phase, 8 no epilogue work, 32 no weight loads, 64 no transform
 };
 
 cudaError_t launch_conv_tc(const ConvParams& p, int num_sms, cudaStream_t stream);

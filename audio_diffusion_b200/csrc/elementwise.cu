@@ -299,19 +299,20 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
 // CIQ_ITER x 256 groups of 4 horizontally adjacent pixels; each group reads its 3 x 6 input patch once (vector load for the
 // aligned middle) and the statistics are reduced once per CTA.  Same FMA order as conv_in_kernel (bit-identical outputs).
 constexpr int CIQ_ITER = 4;
-__global__ void __launch_bounds__(256) conv_in_c1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 2) conv_in_c1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ b, int N, int H, int W, int cout,
                                                          __nv_bfloat16* __restrict__ out, stat_t* __restrict__ stats) {
   __shared__ float red[8][4];
   const Geom g = make_geom(N, H, W);
   const int n = blockIdx.z, pl = blockIdx.y;
-  float wr[8][9], bias[8];
+  float bias[8];
+  f32x2_t w2[4][9];      // (weight of channel 2e, channel 2e+1) per tap
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    bias[e] = __ldg(b + pl * 8 + e);
+  for (int e = 0; e < 8; ++e) bias[e] = __ldg(b + pl * 8 + e);
 #pragma unroll
-    for (int t = 0; t < 9; ++t) wr[e][t] = __ldg(w + (pl * 8 + e) * 9 + t);
-  }
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) w2[e][t] = f2_pack(__ldg(w + (pl * 8 + 2 * e) * 9 + t), __ldg(w + (pl * 8 + 2 * e + 1) * 9 + t));
   const float* xi = x + (long long)n * H * W;
   __nv_bfloat16* plane = out + ((long long)n * (cout >> 3) + pl) * g.PL * 8;
   const int wq = W >> 2, nq = H * wq;
@@ -343,17 +344,30 @@ __global__ void __launch_bounds__(256) conv_in_c1_kernel(const float* __restrict
 #pragma unroll
       for (int c = 0; c < 6; ++c) xv[r][c] = xn[r][c];
     if (it + 1 < CIQ_ITER) load_patch(q + 256, xn);
+    // channel pairs on packed fp32 lanes (FFMA2): 144 + 36 issue slots per 4 pixels instead of 288; each lane is an
+    // IEEE fma in the same order as conv_in_kernel, so the outputs stay bit-identical
+    f32x2_t acc2[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc2[u][e] = f2_pack(bias[2 * e], bias[2 * e + 1]);
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float xs = xv[t / 3][u + t % 3];
+        const f32x2_t x2 = f2_pack(xs, xs);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc2[u][e] = f2_fma(x2, w2[e][t], acc2[u][e]);
+      }
     float acc[4][8];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[u][e] = bias[e];
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[u][e] = fmaf(xv[t / 3][u + t % 3], wr[e][t], acc[u][e]);
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = f2_unpack(acc2[u][e]);
+        acc[u][2 * e] = f.x; acc[u][2 * e + 1] = f.y;
+      }
     __nv_bfloat16* dst = plane + (long long)(g.lead + h * g.Wp + w0) * 8;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -399,155 +413,176 @@ cudaError_t launch_conv_in(const float* x, const float* w, const float* b, int N
 }
 
 // ------------------------------------------------------------- conv_norm_out + SiLU + conv_out + scheduler step
+// HBM-read bound: the kernel streams the raw 128-channel tensor once (halo 1.27x) and writes one fp32 plane.
+// Persistent CTAs (2 per SM) walk 16 x 16 output tiles; per tile the 18 x 18 x C halo goes global -> shared memory with
+// 16-byte cp.async copies (all of a tile's bytes in flight at once, zero-filled outside the image), is normalised +
+// SiLU'd in place (bf16), and the 3x3 conv runs on the warp-level tensor cores (mma.sync m16n8k16: M = 16 pixels of a tile
+// row, N = cout padded to 8, K = 16 channels per tap and k-step).  Weight fragments are built once per CTA.
 constexpr int CO_TILE = 16;
 constexpr int CO_HALO = CO_TILE + 2;
 constexpr int CO_MAXOUT = 4;
+constexpr int CO_CTAS_PER_SM = 2;
 
-__global__ void __launch_bounds__(256) conv_out_kernel(const ConvOutParams p) {
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;   // src-size 0: nothing is read, the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__global__ void __launch_bounds__(256, CO_CTAS_PER_SM) conv_out_kernel(const ConvOutParams p) {
   extern __shared__ __align__(16) uint8_t osm[];
   const int planes = p.C >> 3;
+  constexpr int HV = CO_HALO * CO_HALO;                                         // vectors per plane of the halo tile
   uint4* act = reinterpret_cast<uint4*>(osm);                                   // [planes][324] 16 B vectors
-  uint2* wfrag = reinterpret_cast<uint2*>(osm + (size_t)planes * CO_HALO * CO_HALO * 16);  // [9][C/16][32] B fragments
-  float* scale = reinterpret_cast<float*>(wfrag + 9 * (p.C >> 4) * 32);
-  float* shift = scale + p.C;
-  float* gmean = shift + p.C;
-  float* grstd = gmean + p.groups;
+  uint2* wfrag = reinterpret_cast<uint2*>(osm + (size_t)planes * HV * 16);      // [9][C/16][32] B fragments
+  float2* ssm = reinterpret_cast<float2*>(wfrag + 9 * (p.C >> 4) * 32);         // [C] (scale, shift) of the current sample
+  float* wsm = reinterpret_cast<float*>(act);                                   // [cout][C][9] fp32 weights: build only, aliases the tile
   const Geom g = make_geom(p.N, p.H, p.W);
-  const int n = blockIdx.z;
-  const int h0 = blockIdx.y * CO_TILE, w0 = blockIdx.x * CO_TILE;
-  const int cpg = p.C / p.groups;
+  const int ksteps = p.C >> 4;
+  const int tiles_x = (p.W + CO_TILE - 1) / CO_TILE, tiles_y = (p.H + CO_TILE - 1) / CO_TILE;
+  const int tiles_img = tiles_x * tiles_y, ntiles = tiles_img * p.N;
 
-  for (int gi = threadIdx.x; gi < p.groups; gi += blockDim.x) {
-    double s = 0., q = 0.;
-    for (int c = gi * cpg; c < (gi + 1) * cpg; c += 4) {
-      const stat_t* st = p.stats + ((long long)n * (p.C >> 2) + (c >> 2)) * 2;
-      s += st[0];
-      q += st[1];
-    }
-    const double cnt = (double)cpg * (double)p.H * (double)p.W;
-    const double mean = s / cnt;
-    gmean[gi] = (float)mean;
-    grstd[gi] = (float)(1.0 / sqrt(fmax(q / cnt - mean * mean, 0.) + (double)p.eps));
-  }
   // weights: fp32 [cout][C][3][3] -> per (tap, 16-channel k-step) the m16n8k16 B fragment (k = channel, n = cout padded
   // to 8): lane (g, tq) holds (ch 2tq, 2tq+1 | ch 8+2tq, 9+2tq) of output channel g, zero for g >= cout
-  const int ksteps = p.C >> 4;
+  for (int i = threadIdx.x; i < p.cout * p.C * 9; i += blockDim.x) wsm[i] = __ldg(p.w + i);
+  __syncthreads();
   for (int i = threadIdx.x; i < 9 * ksteps * 32; i += blockDim.x) {
     const int ln = i & 31, ks = (i >> 5) % ksteps, t = i / (32 * ksteps);
     const int co = ln >> 2, tq = ln & 3;
     uint2 bf = make_uint2(0u, 0u);
     if (co < p.cout) {
-      const float* wp = p.w + ((long long)co * p.C + ks * 16 + 2 * tq) * 9 + t;
+      const float* wp = wsm + ((long long)co * p.C + ks * 16 + 2 * tq) * 9 + t;
       bf.x = pack_bf16x2(wp[0], wp[9]);
       bf.y = pack_bf16x2(wp[72], wp[81]);
     }
     wfrag[i] = bf;
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-    const int gi = c / cpg;
-    const float sc = p.gamma[c] * grstd[gi];
-    scale[c] = sc;
-    shift[c] = p.beta[c] - gmean[gi] * sc;
-  }
-  __syncthreads();
-  // normalised + SiLU halo tile (zero outside the image: the conv pads the *activated* tensor)
-  const __nv_bfloat16* img = p.src + (long long)n * planes * g.PL * 8;
-  constexpr int CO_UNR = 5;   // loads in flight per thread: the halo fill is latency-bound otherwise
-  const int total = planes * CO_HALO * CO_HALO;
-  for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * CO_UNR) {
-    uint4 rv[CO_UNR];
-    bool inb[CO_UNR];
-#pragma unroll
-    for (int u = 0; u < CO_UNR; ++u) {
-      const int i = i0 + u * blockDim.x;
-      const int pl = i / (CO_HALO * CO_HALO);
-      const int hp = i - pl * CO_HALO * CO_HALO;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+  const uint32_t act_s = smem_u32(act);
+  const uint32_t* act32 = reinterpret_cast<const uint32_t*>(act);
+  const int total = planes * HV;
+  int cur_n = -1;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n = tile / tiles_img, tr = tile - n * tiles_img;
+    const int ty = tr / tiles_x, tx = tr - ty * tiles_x;
+    const int h0 = ty * CO_TILE, w0 = tx * CO_TILE;
+    __syncthreads();                       // the previous tile's MMAs have read `act` (and wfrag / ssm are complete)
+    // ---- halo tile: every vector of the tile in flight at once
+    const __nv_bfloat16* img = p.src + (long long)n * planes * g.PL * 8;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int pl = i / HV, hp = i - pl * HV;
       const int hy = hp / CO_HALO, hx = hp - hy * CO_HALO;
       const int h = h0 + hy - 1, w = w0 + hx - 1;
-      inb[u] = (i < total) && h >= 0 && h < p.H && w >= 0 && w < p.W;
-      rv[u] = make_uint4(0, 0, 0, 0);
-      if (inb[u]) rv[u] = *reinterpret_cast<const uint4*>(img + ((long long)pl * g.PL + g.lead + h * g.Wp + w) * 8);
+      const bool inb = h >= 0 && h < p.H && w >= 0 && w < p.W;
+      const __nv_bfloat16* sp = img + ((long long)pl * g.PL + g.lead + (inb ? h * g.Wp + w : 0)) * 8;
+      cp_async16_zfill(act_s + (uint32_t)i * 16u, sp, inb);
     }
-#pragma unroll
-    for (int u = 0; u < CO_UNR; ++u) {
-      const int i = i0 + u * blockDim.x;
-      if (i >= total) continue;
-      uint4 o = make_uint4(0, 0, 0, 0);
-      if (inb[u]) {
-        const int pl = i / (CO_HALO * CO_HALO);
-        const uint32_t uu[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
-        uint32_t r[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = unpack_bf16x2(uu[e]);
-          const int c = pl * 8 + 2 * e;
-          r[e] = pack_bf16x2(silu_tanh(f.x * scale[c] + shift[c]), silu_tanh(f.y * scale[c + 1] + shift[c + 1]));
-        }
-        o = make_uint4(r[0], r[1], r[2], r[3]);
-      }
-      act[i] = o;
-    }
-  }
-  __syncthreads();
-  // implicit GEMM on the warp-level tensor cores: M = 16 pixels of one tile row, N = 8 (cout padded), K = 16 channels per
-  // (tap, k-step).  Warp w owns tile rows 2w and 2w+1; A fragments are 32-bit reads of the activated halo tile.
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
-  const uint32_t* act32 = reinterpret_cast<const uint32_t*>(act);
-  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  for (int ks = 0; ks < ksteps; ++ks) {
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int kh = t / 3, kw = t - kh * 3;
-      const uint2 bf = wfrag[(t * ksteps + ks) * 32 + lane];
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int v0 = (2 * ks) * CO_HALO * CO_HALO + (2 * warp + r + kh) * CO_HALO + gq + kw;  // 16-byte vector index
-        const uint32_t a0 = act32[v0 * 4 + tq], a1 = act32[(v0 + 8) * 4 + tq];
-        const uint32_t a2 = act32[(v0 + CO_HALO * CO_HALO) * 4 + tq], a3 = act32[(v0 + CO_HALO * CO_HALO + 8) * 4 + tq];
-        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                     : "+f"(acc[r][0]), "+f"(acc[r][1]), "+f"(acc[r][2]), "+f"(acc[r][3])
-                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf.x), "r"(bf.y));
-      }
-    }
-  }
-  // accumulator (r, 2j + cc) = pixel (row 2w + r, column gq + 8j), output channel 2tq + cc
-#pragma unroll
-  for (int r = 0; r < 2; ++r)
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int h = h0 + 2 * warp + r, w = w0 + gq + 8 * j;
-      if (h >= p.H || w >= p.W) continue;
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int co = 2 * tq + cc;
-        if (co >= p.cout) continue;
-        const float e = acc[r][2 * j + cc] + p.b[co];
-        const long long idx = (((long long)n * p.cout + co) * p.H + h) * p.W + w;
-        if (p.eps_out) p.eps_out[idx] = e;
-        if (p.x_out) {
-          const float xv = p.x[idx];
-          float x0 = (xv - p.coef.sqrt_1m_at * e) * p.coef.inv_sqrt_at;
-          if (p.coef.do_clip) x0 = fminf(fmaxf(x0, -p.coef.clip), p.coef.clip);
-          float rr = p.coef.c_x0 * x0 + p.coef.c_xt * xv + p.coef.c_eps * e;
-          if (p.z) rr += p.coef.c_z * p.z[idx];
-          p.x_out[idx] = rr;
+    if (n != cur_n) {                      // per-sample GroupNorm scale / shift
+      cur_n = n;
+      if (p.ss) {
+        for (int c = threadIdx.x; c < p.C; c += blockDim.x) ssm[c] = __ldg(p.ss + (long long)n * p.C + c);
+      } else {                             // stand-alone use: finalize the statistics here
+        const int cpg = p.C / p.groups;
+        for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+          const int gi = c / cpg;
+          double sm = 0., sq = 0.;
+          for (int cc = gi * cpg; cc < (gi + 1) * cpg; cc += 4) {
+            const stat_t* st = p.stats + ((long long)n * (p.C >> 2) + (cc >> 2)) * 2;
+            sm += st[0];
+            sq += st[1];
+          }
+          const double cnt = (double)cpg * (double)p.H * (double)p.W;
+          const double mean = sm / cnt;
+          const float rstd = (float)(1.0 / sqrt(fmax(sq / cnt - mean * mean, 0.) + (double)p.eps));
+          const float sc = p.gamma[c] * rstd;
+          ssm[c] = make_float2(sc, p.beta[c] - (float)mean * sc);
         }
       }
     }
+    cp_async_wait_all();
+    __syncthreads();
+    // ---- GroupNorm + SiLU in place (zero outside the image: the conv pads the *activated* tensor)
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int pl = i / HV, hp = i - pl * HV;
+      const int hy = hp / CO_HALO, hx = hp - hy * CO_HALO;
+      const int h = h0 + hy - 1, w = w0 + hx - 1;
+      if (h < 0 || h >= p.H || w < 0 || w >= p.W) continue;
+      const uint4 v = act[i];
+      const uint32_t uu[4] = {v.x, v.y, v.z, v.w};
+      uint32_t r[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16x2(uu[e]);
+        const float2 s0 = ssm[pl * 8 + 2 * e], s1 = ssm[pl * 8 + 2 * e + 1];
+        r[e] = pack_bf16x2(silu_tanh(fmaf(f.x, s0.x, s0.y)), silu_tanh(fmaf(f.y, s1.x, s1.y)));
+      }
+      act[i] = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+    __syncthreads();
+    // ---- implicit GEMM: warp w owns tile rows 2w and 2w+1; A fragments are 32-bit reads of the activated halo tile
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    for (int ks = 0; ks < ksteps; ++ks) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int kh = t / 3, kw = t - kh * 3;
+        const uint2 bf = wfrag[(t * ksteps + ks) * 32 + lane];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int v0 = (2 * ks) * HV + (2 * warp + r + kh) * CO_HALO + gq + kw;  // 16-byte vector index
+          const uint32_t a0 = act32[v0 * 4 + tq], a1 = act32[(v0 + 8) * 4 + tq];
+          const uint32_t a2 = act32[(v0 + HV) * 4 + tq], a3 = act32[(v0 + HV + 8) * 4 + tq];
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(acc[r][0]), "+f"(acc[r][1]), "+f"(acc[r][2]), "+f"(acc[r][3])
+                       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf.x), "r"(bf.y));
+        }
+      }
+    }
+    // accumulator (r, 2j + cc) = pixel (row 2w + r, column gq + 8j), output channel 2tq + cc
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int h = h0 + 2 * warp + r, w = w0 + gq + 8 * j;
+        if (h >= p.H || w >= p.W) continue;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int co = 2 * tq + cc;
+          if (co >= p.cout) continue;
+          const float e = acc[r][2 * j + cc] + p.b[co];
+          const long long idx = (((long long)n * p.cout + co) * p.H + h) * p.W + w;
+          if (p.eps_out) p.eps_out[idx] = e;
+          if (p.x_out) {
+            const float xv = p.x[idx];
+            float x0 = (xv - p.coef.sqrt_1m_at * e) * p.coef.inv_sqrt_at;
+            if (p.coef.do_clip) x0 = fminf(fmaxf(x0, -p.coef.clip), p.coef.clip);
+            float rr = p.coef.c_x0 * x0 + p.coef.c_xt * xv + p.coef.c_eps * e;
+            if (p.z) rr += p.coef.c_z * p.z[idx];
+            p.x_out[idx] = rr;
+          }
+        }
+      }
+  }
 }
 
 cudaError_t launch_conv_out(const ConvOutParams& p, cudaStream_t s) {
   if (p.cout > CO_MAXOUT || (p.C & 15)) return cudaErrorInvalidValue;
   const size_t smem = (size_t)(p.C >> 3) * CO_HALO * CO_HALO * 16 + (size_t)9 * (p.C >> 4) * 32 * sizeof(uint2) +
-                      ((size_t)2 * p.C + 2 * p.groups) * sizeof(float);
+                      (size_t)p.C * sizeof(float2);
   static size_t smem_set = 0;
+  static int sms = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     smem_set = smem;
   }
-  dim3 grid((p.W + CO_TILE - 1) / CO_TILE, (p.H + CO_TILE - 1) / CO_TILE, p.N);
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int ntiles = ((p.W + CO_TILE - 1) / CO_TILE) * ((p.H + CO_TILE - 1) / CO_TILE) * p.N;
+  const int grid = ntiles < sms * CO_CTAS_PER_SM ? ntiles : sms * CO_CTAS_PER_SM;
   conv_out_kernel<<<grid, 256, smem, s>>>(p);
   return cudaGetLastError();
 }

@@ -99,6 +99,7 @@ struct StepCoef {
 struct ConvOutParams {
   const __nv_bfloat16* src;   // raw PF8, C channels
   const stat_t* stats;        // [N][C/4][2]
+  const float2* ss;           // [N][C] GroupNorm (scale, shift), finalised by the producer's last CTA; null: use stats here
   const float* gamma;
   const float* beta;
   const float* w;             // fp32 [cout][C][3][3]
@@ -130,10 +131,18 @@ cudaError_t launch_pf8_to_nchw(const __nv_bfloat16* src, float* dst, int N, int 
 cudaError_t launch_temb(const float* t, int N, int dim0, const float* w1, const float* b1, const float* w2,
                         const float* b2, float* temb_act, const float* wcat, const float* bcat, int rows,
                         float* proj, cudaStream_t s, float* save_emb = nullptr, float* save_u1 = nullptr,
-                        float* save_u2 = nullptr);
+                        float* save_u2 = nullptr, int* lead = nullptr);   // lead [N] scratch: share the work of equal timesteps
 
 // self-attention core on the fused qkv tensor (PF8, 3*C channels: q | k | v; head_dim 8 = one plane per head).
 cudaError_t launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int N, int C, int H, int W, cudaStream_t s);
+
+// transformer blocks of the conditional U-Net (cond_ops.cu)
+cudaError_t launch_layernorm_pf8(const __nv_bfloat16* src, __nv_bfloat16* dst, const float* gamma, const float* beta, int N,
+                                 int C, int H, int W, float eps, cudaStream_t s);
+cudaError_t launch_geglu_pf8(const __nv_bfloat16* src, __nv_bfloat16* dst, int N, int Ch, int H, int W, cudaStream_t s);
+cudaError_t launch_cross_attn_vec(const float* enc, const float* wv, const float* wo, const float* bo, float* vec, int N, int C,
+                                  int X, cudaStream_t s);
+cudaError_t launch_mha_flash(const __nv_bfloat16* qkv, __nv_bfloat16* out, int N, int C, int heads, int H, int W, cudaStream_t s);
 
 // generic single-head attention over the fused qkv tensor (AutoencoderKL mid block); scores: N * seq * seq floats of scratch
 cudaError_t launch_attention_1head(const __nv_bfloat16* qkv, __nv_bfloat16* out, float* scores, int N, int C, int H, int W,

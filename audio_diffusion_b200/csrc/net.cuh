@@ -34,7 +34,9 @@ struct Act {  // PF8 activation tensor
 };
 
 enum OpKind { OP_TEMB, OP_CONV_IN, OP_GN, OP_CONV, OP_UPSAMPLE, OP_PARITY, OP_ATTN, OP_CONV_OUT,
-              OP_ATTN1 /* single head of dim C */, OP_VAE_SAMPLE, OP_MIX1X1 };
+              OP_ATTN1 /* single head of dim C */, OP_VAE_SAMPLE, OP_MIX1X1,
+              OP_LN /* LayerNorm over channels */, OP_GEGLU, OP_MHA /* multi-head attention, head_dim 16/32/64 */,
+              OP_XVEC /* cross-attention against a one-token encoding = per-sample vector */ };
 struct Op {
   OpKind kind;
   ConvParams conv;
@@ -48,7 +50,10 @@ struct Op {
   float* f0 = nullptr;   // OP_ATTN1: score scratch; OP_MIX1X1: fp32 destination
   const float* fw = nullptr;  // OP_CONV_IN / OP_VAE_SAMPLE / OP_MIX1X1: fp32 weight and bias
   const float* fb = nullptr;
+  const float* fc = nullptr;  // OP_XVEC: to_out bias
+  float* f1 = nullptr;        // OP_XVEC: destination [N][C]
   int cin = 0;
+  float eps = 0.f;            // OP_LN
 };
 
 struct Bump {  // two-pass bump allocator: base == nullptr computes sizes only
@@ -97,11 +102,14 @@ struct NetBase {
   size_t stats_bytes = 0;
   float* temb_act = nullptr;
   float* temb_proj = nullptr;
+  int* temb_lead = nullptr;         // [N] first sample with the same timestep (inference only)
   bool training = false;            // keep every activation (no pooling) and the timestep-MLP pre-activations for backward
   float* temb_emb = nullptr;        // [N][dim0]      sinusoid
   float* temb_u1 = nullptr;         // [N][4 dim0]    linear_1 output before SiLU
   float* temb_u2 = nullptr;         // [N][4 dim0]    linear_2 output before SiLU
   int num_sms = 148;
+  const float* enc = nullptr;       // conditional U-Net: encoder_hidden_states [N][enc_S][X] of the next forward
+  int enc_S = 0;
   int last_launches = 0;
   PackBatch pack_batch;             // device job table of the weight packing (one launch for all K-segments)
 };
@@ -241,6 +249,39 @@ static void layout_attn(NetBase* h, Bump& b, const std::string& n, int ch) {
   need_ident(h, b, ch);
 }
 
+// Transformer2DModel + BasicTransformerBlock of the conditional U-Net (diffusers naming): packed 1x1 projections
+static void p_transformer(NetBase* h, const std::string& n, int c, int X) {
+  p_gn(h, n + ".norm", c);
+  p_conv(h, n + ".proj_in", c, c, 1);
+  const std::string b = n + ".transformer_blocks.0";
+  p_gn(h, b + ".norm1", c);
+  add_param(h, b + ".attn1.to_q.weight", {c, c});
+  add_param(h, b + ".attn1.to_k.weight", {c, c});
+  add_param(h, b + ".attn1.to_v.weight", {c, c});
+  p_lin(h, b + ".attn1.to_out.0", c, c);
+  p_gn(h, b + ".norm2", c);
+  add_param(h, b + ".attn2.to_q.weight", {c, c});
+  add_param(h, b + ".attn2.to_k.weight", {c, X});
+  add_param(h, b + ".attn2.to_v.weight", {c, X});
+  p_lin(h, b + ".attn2.to_out.0", c, c);
+  p_gn(h, b + ".norm3", c);
+  p_lin(h, b + ".ff.net.0.proj", c, 8 * c);
+  p_lin(h, b + ".ff.net.2", 4 * c, c);
+  p_conv(h, n + ".proj_out", c, c, 1);
+}
+static void layout_transformer(NetBase* h, Bump& b, const std::string& n, int c) {
+  const std::string t = n + ".transformer_blocks.0";
+  add_job(h, b, n + ".proj_in#0", n + ".proj_in.weight", c, c, 1, 0, c, taps_1x1());
+  add_job(h, b, t + ".qkv#q", t + ".attn1.to_q.weight", c, c, 1, 0, c, taps_1x1());   // q | k | v blocks are contiguous
+  add_job(h, b, t + ".qkv#k", t + ".attn1.to_k.weight", c, c, 1, 0, c, taps_1x1());
+  add_job(h, b, t + ".qkv#v", t + ".attn1.to_v.weight", c, c, 1, 0, c, taps_1x1());
+  add_job(h, b, t + ".attn1.out#0", t + ".attn1.to_out.0.weight", c, c, 1, 0, c, taps_1x1());
+  add_job(h, b, t + ".ff1#0", t + ".ff.net.0.proj.weight", 8 * c, c, 1, 0, c, taps_1x1());
+  add_job(h, b, t + ".ff2#0", t + ".ff.net.2.weight", c, 4 * c, 1, 0, 4 * c, taps_1x1());
+  add_job(h, b, n + ".proj_out#0", n + ".proj_out.weight", c, c, 1, 0, c, taps_1x1());
+  need_ident(h, b, c);
+}
+
 static __global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) o[i] = a[i] + (b ? b[i] : 0.f);
@@ -360,9 +401,32 @@ struct Builder {
 
   // GroupNorm over cat(a, b): statistics -> per-(sample, channel) scale/shift; the apply itself is fused into the consumer
   // conv's transform warps. Returns the [N][Ca + Cb] scale/shift array.
-  float2* gn_finalize(const Act& a, const Act* b, const std::string& norm) {
+  // Let the launch just planned (the producer of `a`; `b`, a skip connection, is older) finalize the GroupNorm over
+  // cat(a, b) in its last CTA.  Returns the [N][Ca + Cb] (scale, shift) array, or nullptr if the last op cannot do it
+  // (conv_in, an op of another kind, a batch too large for the scratch).
+  float2* gn_attach(const Act& a, const Act* b, const std::string& norm, float2* ss = nullptr, float eps = -1.f) {
+    const int Ct = a.C + (b ? b->C : 0);
+    static const bool off = [] { const char* e = getenv("B200AD_NO_GNFOLD"); return e && e[0] == '1'; }();   // A/B switch
+    if (off) return nullptr;
+    if (plan->empty() || plan->back().kind != OP_CONV || plan->back().conv.out != a.p || plan->back().conv.fin.ss ||
+        (size_t)N * h->norm_groups * 2 * sizeof(float) > 32768)
+      return nullptr;
+    if (!ss) ss = (float2*)ws.take((size_t)N * Ct * sizeof(float2));
+    ConvGnFin& f = plan->back().conv.fin;
+    f.stats[0] = a.stats; f.C[0] = a.C;
+    f.stats[1] = b ? b->stats : nullptr; f.C[1] = b ? b->C : 0;
+    f.gamma = P(norm + ".weight"); f.beta = P(norm + ".bias");
+    f.ss = ss;
+    f.counter = (unsigned*)ws.take(sizeof(unsigned));
+    f.groups = h->norm_groups; f.HW = a.H * a.W; f.eps = eps < 0.f ? h->norm_eps : eps;
+    return ss;
+  }
+  float2* gn_attach(const Act& a, const std::string& norm) { return gn_attach(a, nullptr, norm); }
+
+  float2* gn_finalize(const Act& a, const Act* b, const std::string& norm, float eps = -1.f) {
     const int Ct = a.C + (b ? b->C : 0);
     float2* ss = (float2*)ws.take((size_t)N * Ct * sizeof(float2));
+    if (gn_attach(a, b, norm, ss, eps)) return ss;
     Op op{};
     op.kind = OP_GN;
     GnApplyParams& p = op.gn;
@@ -370,7 +434,7 @@ struct Builder {
     p.src[1] = b ? b->p : nullptr; p.stats[1] = b ? b->stats : nullptr; p.C[1] = b ? b->C : 0;
     p.gamma = P(norm + ".weight"); p.beta = P(norm + ".bias");
     p.dst = nullptr;
-    p.N = N; p.H = a.H; p.W = a.W; p.groups = h->norm_groups; p.eps = h->norm_eps; p.silu = 0;
+    p.N = N; p.H = a.H; p.W = a.W; p.groups = h->norm_groups; p.eps = eps < 0.f ? h->norm_eps : eps; p.silu = 0;
     op.ss = ss;
     plan->push_back(op);
     return ss;
@@ -441,6 +505,146 @@ struct Builder {
     h->taps[n + ".h1"] = h1;
     h->taps[n] = out;
     return out;
+  }
+
+  // plain 1-tap conv (a linear layer over the pixel tokens) with optional fused GroupNorm of the source, identity residual
+  // and per-sample additive vector
+  void linear(const Act& out, const Act& src, const std::string& wkey, const float* bias, const float2* ss = nullptr,
+              const Act* residual = nullptr, const float* vec = nullptr, int vec_stride = 0) {
+    Op op{};
+    op.kind = OP_CONV;
+    ConvParams& p = op.conv;
+    conv_common(p, out);
+    p.nseg = 1;
+    set_seg(p.seg[0], src.p, src.C, src.H, src.W, WP(wkey), taps_1x1());
+    if (ss) seg_norm(p.seg[0], ss, src.C, false);
+    if (residual) {
+      set_seg(p.seg[1], residual->p, residual->C, residual->H, residual->W, IDENT(residual->C), taps_1x1());
+      p.nseg = 2;
+    }
+    p.bias = bias;
+    p.temb = vec; p.temb_stride = vec_stride;
+    plan->push_back(op);
+  }
+
+  // Transformer2DModel with one BasicTransformerBlock (conditional U-Net), encoder sequence length 1:
+  //   h0 = proj_in(GroupNorm(x));  h2 = h0 + attn1(LN1(h0)) + attn2(enc);  h3 = h2 + ff(LN3(h2));  out = proj_out(h3) + x
+  // attn2 with ONE key is the per-sample vector to_out(to_v(enc)) (softmax over a single key is 1): it rides on the
+  // per-sample additive term of the attn1 output projection.
+  Act transformer(const std::string& n, const Act& x, int heads, int X, bool out_pooled, const std::string& out_tag) {
+    const int C = x.C, H = x.H, W = x.W;
+    const std::string t = n + ".transformer_blocks.0";
+    const float2* ssx = gn_finalize(x, nullptr, n + ".norm", 1e-6f);
+    float* vec = (float*)ws.take((size_t)N * C * sizeof(float));
+    {
+      Op op{};
+      op.kind = OP_XVEC;
+      op.C = C; op.cin = X;
+      op.fw = P(t + ".attn2.to_v.weight"); op.fb = P(t + ".attn2.to_out.0.weight"); op.fc = P(t + ".attn2.to_out.0.bias");
+      op.f1 = vec;
+      plan->push_back(op);
+    }
+    Act h0 = pooled("tf_h0", C, H, W, false);
+    linear(h0, x, n + ".proj_in#0", P(n + ".proj_in.bias"), ssx);
+    Act n1 = pooled("tf_ln", C, H, W, false);
+    auto layer_norm = [&](const Act& src, const Act& dst, const std::string& nm) {
+      Op op{};
+      op.kind = OP_LN;
+      op.src = src.p; op.dst = dst.p; op.C = C; op.H = H; op.W = W;
+      op.fw = P(nm + ".weight"); op.fb = P(nm + ".bias"); op.eps = 1e-5f;
+      plan->push_back(op);
+    };
+    layer_norm(h0, n1, t + ".norm1");
+    Act qkv = pooled("tf_qkv", 3 * C, H, W, false);
+    linear(qkv, n1, t + ".qkv#q", nullptr);
+    Act ao = pooled("tf_ao", C, H, W, false);
+    {
+      Op op{};
+      op.kind = OP_MHA;
+      op.src = qkv.p; op.dst = ao.p; op.C = C; op.H = H; op.W = W; op.cin = heads;
+      plan->push_back(op);
+    }
+    Act h2 = pooled("tf_h2", C, H, W, false);
+    linear(h2, ao, t + ".attn1.out#0", P(t + ".attn1.to_out.0.bias"), nullptr, &h0, vec, C);
+    layer_norm(h2, n1, t + ".norm3");
+    Act ff1 = pooled("tf_ff1", 8 * C, H, W, false);
+    linear(ff1, n1, t + ".ff1#0", P(t + ".ff.net.0.proj.bias"));
+    Act gg = pooled("tf_gg", 4 * C, H, W, false);
+    {
+      Op op{};
+      op.kind = OP_GEGLU;
+      op.src = ff1.p; op.dst = gg.p; op.C = 4 * C; op.H = H; op.W = W;
+      plan->push_back(op);
+    }
+    Act h3 = pooled("tf_h0", C, H, W, false);     // h0 is dead after h2
+    linear(h3, gg, t + ".ff2#0", P(t + ".ff.net.2.bias"), nullptr, &h2);
+    Act out = out_pooled ? pooled(out_tag, C, H, W, true) : alloc(C, H, W, true);
+    linear(out, h3, n + ".proj_out#0", P(n + ".proj_out.bias"), nullptr, &x);
+    h->taps[n + ".attn2"] = h2;
+    h->taps[n] = out;
+    return out;
+  }
+
+  // Downsample2D(use_conv, padding 1): 3x3 stride-2 conv = four K-segments over the parity planes of the input
+  Act down2(const std::string& n, const Act& x) {
+    const int C = x.C, Ho = x.H / 2, Wo = x.W / 2;
+    const Geom go = make_geom(N, Ho, Wo);
+    const size_t tsz = (size_t)N * (C / 8) * go.PL * 8;  // elements per parity tensor
+    Act par = pooled("parity", 4 * C, Ho, Wo, false);     // 4 tensors back to back (same bytes as 4C channels)
+    h->taps[n + ".parity"] = par;
+    {
+      Op op{};
+      op.kind = OP_PARITY;
+      op.src = x.p; op.dst = par.p; op.C = C; op.H = x.H; op.W = x.W;
+      plan->push_back(op);
+    }
+    Act y = alloc(C, Ho, Wo, true);
+    Op op{};
+    op.kind = OP_CONV;
+    ConvParams& p = op.conv;
+    conv_common(p, y);
+    p.nseg = 4;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        set_seg(p.seg[a * 2 + b], par.p + (size_t)(a * 2 + b) * tsz, C, Ho, Wo, WP(n + S("#%d", a * 2 + b)), taps_parity(a, b), true);
+    p.bias = P(n + ".bias");
+    p.temb = nullptr; p.temb_stride = 0;
+    plan->push_back(op);
+    h->taps[n] = y;
+    return y;
+  }
+
+  // Upsample2D(use_conv): nearest-2x + 3x3 conv folded into four 2x2 convs on the low-res tensor (one launch per parity)
+  Act up2(const std::string& nm, const Act& x) {
+    const int C = x.C, hh = x.H, ww = x.W;
+    Act y = pooled("up_conv", C, hh * 2, ww * 2, true);
+    for (int pa = 0; pa < 2; ++pa)
+      for (int pb = 0; pb < 2; ++pb) {
+        const UpTaps ut = taps_up2(pa, pb);
+        Op op{};
+        op.kind = OP_CONV;
+        ConvParams& p = op.conv;
+        Act lo = y;                       // item geometry = low-res input geometry, output tensor = y
+        lo.H = hh; lo.W = ww;
+        conv_common(p, lo);
+        p.up2 = 1; p.oy = pa; p.ox = pb;
+        p.nseg = 1;
+        ConvSeg& sgm = p.seg[0];
+        set_seg(sgm, x.p, C, hh, ww, WP(nm + S("#p%d", pa * 2 + pb)), ut.pack);
+        sgm.ht = sgm.hb = sgm.hl = sgm.hr = 0;
+        for (int t = 0; t < 4; ++t) {
+          sgm.dh[t] = ut.dh[t]; sgm.dw[t] = ut.dw[t];
+          if (ut.dh[t] < 0) sgm.ht = 1;
+          if (ut.dh[t] > 0) sgm.hb = 1;
+          if (ut.dw[t] < 0) sgm.hl = 1;
+          if (ut.dw[t] > 0) sgm.hr = 1;
+        }
+        p.bias = P(nm + ".bias");
+        p.temb = nullptr; p.temb_stride = 0;
+        plan->push_back(op);
+      }
+    h->taps[nm] = y;
+    return y;
   }
 
   Act attention(const std::string& n, const Act& x, bool out_pooled, const std::string& out_tag) {

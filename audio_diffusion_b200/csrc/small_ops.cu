@@ -19,12 +19,26 @@ __global__ void __launch_bounds__(256) temb_mlp_kernel(const float* __restrict__
                                                        const float* __restrict__ b1, const float* __restrict__ w2,
                                                        const float* __restrict__ b2, float* __restrict__ temb_act,
                                                        float* __restrict__ save_emb, float* __restrict__ save_u1,
-                                                       float* __restrict__ save_u2) {
+                                                       float* __restrict__ save_u2, int* __restrict__ lead) {
   extern __shared__ float tsm[];
   float* emb = tsm;          // dim0
   float* h1 = tsm + dim0;    // 4*dim0
   const int n = blockIdx.x, D = 4 * dim0, half = dim0 / 2;
   const float tv = t[n];
+  if (lead) {
+    // Samples that share a timestep share the whole embedding (the sampling loop passes ONE t for the batch,
+    // pipeline_audio_diffusion.py:163): only the first sample of each class ("leader") is computed, the projection kernel
+    // copies its rows to the others.  lead == nullptr (training: per-sample t, activations saved for backward): no sharing.
+    __shared__ int s_lead;
+    if (threadIdx.x == 0) {
+      int m = 0;
+      while (m < n && t[m] != tv) ++m;
+      s_lead = m;
+      lead[n] = m;
+    }
+    __syncthreads();
+    if (s_lead != n) return;
+  }
   for (int i = threadIdx.x; i < half; i += blockDim.x) {
     const float freq = expf(-logf(10000.0f) * (float)i / (float)half);
     const float a = tv * freq;
@@ -58,7 +72,7 @@ __global__ void __launch_bounds__(256) temb_mlp_kernel(const float* __restrict__
 // one warp per projection row, all samples
 __global__ void __launch_bounds__(256) temb_proj_kernel(const float* __restrict__ temb_act, int N, int D,
                                                         const float* __restrict__ wcat, const float* __restrict__ bcat,
-                                                        int rows, float* __restrict__ proj) {
+                                                        int rows, float* __restrict__ proj, const int* __restrict__ lead) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + warp;
   if (r >= rows) return;
@@ -67,22 +81,27 @@ __global__ void __launch_bounds__(256) temb_proj_kernel(const float* __restrict_
   for (int k = 0; k < per; ++k) wv[k] = wcat[(long long)r * D + k * 32 + lane];
   const float bias = bcat[r];
   for (int n = 0; n < N; ++n) {
-    float s = 0.f;
-    for (int k = 0; k < per; ++k) s += wv[k] * temb_act[(long long)n * D + k * 32 + lane];
-    s = warp_sum(s);
-    if (lane == 0) proj[(long long)n * rows + r] = s + bias;
+    const int ld = lead ? lead[n] : n;
+    if (ld == n) {
+      float s = 0.f;
+      for (int k = 0; k < per; ++k) s += wv[k] * temb_act[(long long)n * D + k * 32 + lane];
+      s = warp_sum(s);
+      if (lane == 0) proj[(long long)n * rows + r] = s + bias;
+    } else if (lane == 0) {      // same timestep as an earlier sample: its row was written by this very lane
+      proj[(long long)n * rows + r] = proj[(long long)ld * rows + r];
+    }
   }
 }
 
 cudaError_t launch_temb(const float* t, int N, int dim0, const float* w1, const float* b1, const float* w2,
                         const float* b2, float* temb_act, const float* wcat, const float* bcat, int rows,
-                        float* proj, cudaStream_t s, float* save_emb, float* save_u1, float* save_u2) {
+                        float* proj, cudaStream_t s, float* save_emb, float* save_u1, float* save_u2, int* lead) {
   const int D = 4 * dim0;
   if (D > 1024 || (D % 32) != 0) return cudaErrorInvalidValue;
-  temb_mlp_kernel<<<N, 256, (dim0 + D) * sizeof(float), s>>>(t, dim0, w1, b1, w2, b2, temb_act, save_emb, save_u1, save_u2);
+  temb_mlp_kernel<<<N, 256, (dim0 + D) * sizeof(float), s>>>(t, dim0, w1, b1, w2, b2, temb_act, save_emb, save_u1, save_u2, lead);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  temb_proj_kernel<<<(rows + 7) / 8, 256, 0, s>>>(temb_act, N, D, wcat, bcat, rows, proj);
+  temb_proj_kernel<<<(rows + 7) / 8, 256, 0, s>>>(temb_act, N, D, wcat, bcat, rows, proj, lead);
   return cudaGetLastError();
 }
 

@@ -34,12 +34,14 @@ static void build_param_table(b200ad_unet* h) {
     for (int j = 0; j < c.layers_per_block; ++j) {
       p_resnet(h, S("down_blocks.%d.resnets.%d", i, j), j == 0 ? in_c : out_c, out_c, temb);
       if (c.down_attn[i]) p_attn(h, S("down_blocks.%d.attentions.%d", i, j), out_c);
+      if (c.down_cross[i]) p_transformer(h, S("down_blocks.%d.attentions.%d", i, j), out_c, c.cross_attention_dim);
     }
     if (i != nb - 1) p_conv(h, S("down_blocks.%d.downsamplers.0.conv", i), out_c, out_c, 3);
   }
   const int mid = c.block_out_channels[nb - 1];
   p_resnet(h, "mid_block.resnets.0", mid, mid, temb);
-  p_attn(h, "mid_block.attentions.0", mid);
+  if (c.cross_attention_dim) p_transformer(h, "mid_block.attentions.0", mid, c.cross_attention_dim);
+  else p_attn(h, "mid_block.attentions.0", mid);
   p_resnet(h, "mid_block.resnets.1", mid, mid, temb);
   out_c = c.block_out_channels[nb - 1];
   for (int i = 0; i < nb; ++i) {
@@ -52,6 +54,7 @@ static void build_param_table(b200ad_unet* h) {
       const int res_in = (j == 0) ? prev_c : out_c;
       p_resnet(h, S("up_blocks.%d.resnets.%d", i, j), res_in + skip_c, out_c, temb);
       if (c.up_attn[i]) p_attn(h, S("up_blocks.%d.attentions.%d", i, j), out_c);
+      if (c.up_cross[i]) p_transformer(h, S("up_blocks.%d.attentions.%d", i, j), out_c, c.cross_attention_dim);
     }
     if (i != nb - 1) p_conv(h, S("up_blocks.%d.upsamplers.0.conv", i), out_c, out_c, 3);
   }
@@ -72,12 +75,14 @@ static void build_packed_layout(b200ad_unet* h) {
   h->ident_off.clear();
   auto resnet = [&](const std::string& n, int ca, int cb, int co) { layout_resnet(h, b, n, ca, cb, co, true); };
   auto attn = [&](const std::string& n, int ch) { layout_attn(h, b, n, ch); };
+  auto xattn = [&](const std::string& n, int ch) { layout_transformer(h, b, n, ch); };
   for (int i = 0; i < nb; ++i) {
     const int in_c = out_c;
     out_c = c.block_out_channels[i];
     for (int j = 0; j < c.layers_per_block; ++j) {
       resnet(S("down_blocks.%d.resnets.%d", i, j), j == 0 ? in_c : out_c, 0, out_c);
       if (c.down_attn[i]) attn(S("down_blocks.%d.attentions.%d", i, j), out_c);
+      if (c.down_cross[i]) xattn(S("down_blocks.%d.attentions.%d", i, j), out_c);
       skip_c.push_back(out_c);
     }
     if (i != nb - 1) {
@@ -90,7 +95,8 @@ static void build_packed_layout(b200ad_unet* h) {
   }
   const int mid = c.block_out_channels[nb - 1];
   resnet("mid_block.resnets.0", mid, 0, mid);
-  attn("mid_block.attentions.0", mid);
+  if (c.cross_attention_dim) xattn("mid_block.attentions.0", mid);
+  else attn("mid_block.attentions.0", mid);
   resnet("mid_block.resnets.1", mid, 0, mid);
   out_c = mid;
   for (int i = 0; i < nb; ++i) {
@@ -103,6 +109,7 @@ static void build_packed_layout(b200ad_unet* h) {
       const int res_in = (j == 0) ? prev_c : out_c;
       resnet(S("up_blocks.%d.resnets.%d", i, j), res_in, sc, out_c);
       if (c.up_attn[i]) attn(S("up_blocks.%d.attentions.%d", i, j), out_c);
+      if (c.up_cross[i]) xattn(S("up_blocks.%d.attentions.%d", i, j), out_c);
     }
     if (i != nb - 1) {
       const std::string nm = S("up_blocks.%d.upsamplers.0.conv", i);
@@ -127,6 +134,13 @@ extern "C" int b200ad_unet_create(const b200ad_unet_config* cfg, b200ad_unet** o
   if (!cfg || !out) return set_err("null argument");
   if (cfg->num_blocks < 1 || cfg->num_blocks > B200AD_MAX_BLOCKS) return set_err("num_blocks out of range");
   if (cfg->attention_head_dim != 8) return set_err("only attention_head_dim == 8 is implemented");
+  if (cfg->cross_attention_dim < 0 || cfg->cross_attention_dim > 4096) return set_err("cross_attention_dim out of range");
+  for (int i = 0; i < cfg->num_blocks; ++i) {
+    if ((cfg->down_cross[i] || cfg->up_cross[i]) && !cfg->cross_attention_dim) return set_err("cross-attention blocks need cross_attention_dim");
+    if ((cfg->down_cross[i] && cfg->down_attn[i]) || (cfg->up_cross[i] && cfg->up_attn[i])) return set_err("a block is either Attn or CrossAttn");
+    const int d = cfg->block_out_channels[i] / 8;    // conditional model: 8 heads, head_dim = channels / 8
+    if ((cfg->down_cross[i] || cfg->up_cross[i]) && d != 16 && d != 32 && d != 64) return set_err("cross-attention blocks need channels / 8 in {16, 32, 64}");
+  }
   for (int i = 0; i < cfg->num_blocks; ++i)
     if (cfg->block_out_channels[i] % 128) return set_err("block_out_channels must be multiples of 128");
   if (cfg->out_channels > 4) return set_err("out_channels > 4 not implemented");
@@ -203,6 +217,7 @@ static int build_plan(b200ad_unet* h, uint8_t* ws_base, int N, int H, int W, siz
     const int D = c.block_out_channels[0] * 4;
     h->temb_act = (float*)B.ws.take((size_t)N * D * 4);
     h->temb_proj = (float*)B.ws.take((size_t)N * h->temb_rows * 4);
+    h->temb_lead = (int*)B.ws.take((size_t)N * 4);
     if (h->training) {
       h->temb_emb = (float*)B.ws.take((size_t)N * c.block_out_channels[0] * 4);
       h->temb_u1 = (float*)B.ws.take((size_t)N * D * 4);
@@ -225,54 +240,28 @@ static int build_plan(b200ad_unet* h, uint8_t* ws_base, int N, int H, int W, siz
     }
     h->taps["conv_in"] = x;
     std::vector<Act> skips{x};
+    const int heads = c.attention_head_dim, X = c.cross_attention_dim;
     for (int i = 0; i < nb; ++i) {
       out_c = c.block_out_channels[i];
       for (int j = 0; j < c.layers_per_block; ++j) {
         const std::string rn = S("down_blocks.%d.resnets.%d", i, j);
-        if (c.down_attn[i]) {
+        const std::string an = S("down_blocks.%d.attentions.%d", i, j);
+        if (c.down_attn[i] || c.down_cross[i]) {
           Act r = B.resnet(rn, x, nullptr, out_c, true, "res_tmp");
-          x = B.attention(S("down_blocks.%d.attentions.%d", i, j), r, false, "");
+          x = c.down_cross[i] ? B.transformer(an, r, heads, X, false, "") : B.attention(an, r, false, "");
         } else {
           x = B.resnet(rn, x, nullptr, out_c, false, "");
         }
         skips.push_back(x);
       }
       if (i != nb - 1) {
-        const std::string n = S("down_blocks.%d.downsamplers.0.conv", i);
-        const int Ho = hh / 2, Wo = ww / 2;
-        const Geom go = make_geom(N, Ho, Wo);
-        const size_t tsz = (size_t)N * (out_c / 8) * go.PL * 8;  // elements per parity tensor
-        Act par = B.pooled("parity", 4 * out_c, Ho, Wo, false);  // 4 tensors back to back (same bytes as 4C channels)
-        h->taps[n + ".parity"] = par;
-        {
-          Op op{};
-          op.kind = OP_PARITY;
-          op.src = x.p; op.dst = par.p; op.C = out_c; op.H = hh; op.W = ww;
-          plan.push_back(op);
-        }
-        Act y = B.alloc(out_c, Ho, Wo, true);
-        {
-          Op op{};
-          op.kind = OP_CONV;
-          ConvParams& p = op.conv;
-          B.conv_common(p, y);
-          p.nseg = 4;
-          for (int a = 0; a < 2; ++a)
-            for (int b = 0; b < 2; ++b)
-              B.set_seg(p.seg[a * 2 + b], par.p + (size_t)(a * 2 + b) * tsz, out_c, Ho, Wo,
-                        B.WP(n + S("#%d", a * 2 + b)), taps_parity(a, b), true);
-          p.bias = B.P(n + ".bias");
-          p.temb = nullptr; p.temb_stride = 0;
-          plan.push_back(op);
-        }
-        h->taps[n] = y;
-        x = y;
-        hh = Ho; ww = Wo;
+        x = B.down2(S("down_blocks.%d.downsamplers.0.conv", i), x);
+        hh /= 2; ww /= 2;
         skips.push_back(x);
       }
     }
     x = B.resnet("mid_block.resnets.0", x, nullptr, out_c, true, "res_tmp");
-    x = B.attention("mid_block.attentions.0", x, true, "up_a");
+    x = X ? B.transformer("mid_block.attentions.0", x, heads, X, true, "up_a") : B.attention("mid_block.attentions.0", x, true, "up_a");
     x = B.resnet("mid_block.resnets.1", x, nullptr, out_c, true, "up_b");
     int flip = 0;
     for (int i = 0; i < nb; ++i) {
@@ -282,45 +271,18 @@ static int build_plan(b200ad_unet* h, uint8_t* ws_base, int N, int H, int W, siz
         Act sk = skips.back();
         skips.pop_back();
         const std::string rn = S("up_blocks.%d.resnets.%d", i, j);
-        if (c.up_attn[i]) {
+        const std::string an = S("up_blocks.%d.attentions.%d", i, j);
+        if (c.up_attn[i] || c.up_cross[i]) {
           Act r = B.resnet(rn, x, &sk, out_c, true, "res_tmp");
-          x = B.attention(S("up_blocks.%d.attentions.%d", i, j), r, true, (flip++ & 1) ? "up_b" : "up_a");
+          const char* tag = (flip++ & 1) ? "up_b" : "up_a";
+          x = c.up_cross[i] ? B.transformer(an, r, heads, X, true, tag) : B.attention(an, r, true, tag);
         } else {
           x = B.resnet(rn, x, &sk, out_c, true, (flip++ & 1) ? "up_b" : "up_a");
         }
       }
       if (i != nb - 1) {
-        const std::string nm = S("up_blocks.%d.upsamplers.0.conv", i);
-        // nearest-2x + 3x3 conv folded into four 2x2 convs on the low-res tensor (one launch per output parity)
-        Act y = B.pooled("up_conv", out_c, hh * 2, ww * 2, true);
-        for (int pa = 0; pa < 2; ++pa)
-          for (int pb = 0; pb < 2; ++pb) {
-            const UpTaps ut = taps_up2(pa, pb);
-            Op op{};
-            op.kind = OP_CONV;
-            ConvParams& p = op.conv;
-            Act lo = y;                       // item geometry = low-res input geometry, output tensor = y
-            lo.H = hh; lo.W = ww;
-            B.conv_common(p, lo);
-            p.up2 = 1; p.oy = pa; p.ox = pb;
-            p.nseg = 1;
-            ConvSeg& sgm = p.seg[0];
-            B.set_seg(sgm, x.p, out_c, hh, ww, B.WP(nm + S("#p%d", pa * 2 + pb)), ut.pack);
-            sgm.ht = sgm.hb = sgm.hl = sgm.hr = 0;
-            for (int t = 0; t < 4; ++t) {
-              sgm.dh[t] = ut.dh[t]; sgm.dw[t] = ut.dw[t];
-              if (ut.dh[t] < 0) sgm.ht = 1;
-              if (ut.dh[t] > 0) sgm.hb = 1;
-              if (ut.dw[t] < 0) sgm.hl = 1;
-              if (ut.dw[t] > 0) sgm.hr = 1;
-            }
-            p.bias = B.P(nm + ".bias");
-            p.temb = nullptr; p.temb_stride = 0;
-            plan.push_back(op);
-          }
+        x = B.up2(S("up_blocks.%d.upsamplers.0.conv", i), x);
         hh *= 2; ww *= 2;
-        h->taps[nm] = y;
-        x = y;
       }
     }
     {
@@ -328,6 +290,7 @@ static int build_plan(b200ad_unet* h, uint8_t* ws_base, int N, int H, int W, siz
       op.kind = OP_CONV_OUT;
       ConvOutParams& p = op.co;
       p.src = x.p; p.stats = x.stats;
+      p.ss = B.gn_attach(x, "conv_norm_out");     // finalised by the last up-block conv's last CTA (null: in conv_out)
       p.gamma = B.P("conv_norm_out.weight"); p.beta = B.P("conv_norm_out.bias");
       p.w = B.P("conv_out.weight"); p.b = B.P("conv_out.bias");
       p.N = N; p.C = x.C; p.H = hh; p.W = ww; p.cout = c.out_channels; p.groups = c.norm_num_groups; p.eps = c.norm_eps;
@@ -352,13 +315,13 @@ extern "C" size_t b200ad_unet_workspace_bytes(const b200ad_unet* hc, int N, int 
   // dry run on a scratch copy of the mutable plan state
   auto saved_plan = h->plan;
   auto saved_taps = h->taps;
-  stat_t* sa = h->stats_arena; size_t sb = h->stats_bytes; float* ta = h->temb_act; float* tp = h->temb_proj;
+  stat_t* sa = h->stats_arena; size_t sb = h->stats_bytes; float* ta = h->temb_act; float* tp = h->temb_proj; int* tl = h->temb_lead;
   float* te = h->temb_emb; float* tu1 = h->temb_u1; float* tu2 = h->temb_u2;
   uint8_t* saved_packed = h->packed;
   std::vector<const float*> saved_pptr = h->pptr;
   size_t bytes = 0;
   build_plan(h, nullptr, N, H, W, &bytes);
-  h->plan = saved_plan; h->taps = saved_taps; h->stats_arena = sa; h->stats_bytes = sb; h->temb_act = ta; h->temb_proj = tp;
+  h->plan = saved_plan; h->taps = saved_taps; h->stats_arena = sa; h->stats_bytes = sb; h->temb_act = ta; h->temb_proj = tp; h->temb_lead = tl;
   h->packed = saved_packed; h->pptr = saved_pptr;
   h->temb_emb = te; h->temb_u1 = tu1; h->temb_u2 = tu2;
   return bytes;
@@ -397,7 +360,7 @@ static int run_plan(b200ad_unet* h, const float* x, const float* t, const float*
                        h->pptr[h->pidx.at("time_embedding.linear_2.bias")], h->temb_act,
                        (const float*)(h->packed + h->off_wcat), (const float*)(h->packed + h->off_bcat), h->temb_rows,
                        h->temb_proj, st, h->training ? h->temb_emb : nullptr, h->training ? h->temb_u1 : nullptr,
-                       h->training ? h->temb_u2 : nullptr));
+                       h->training ? h->temb_u2 : nullptr, h->training ? nullptr : h->temb_lead));
         launches += 2;
         break;
       }
@@ -424,6 +387,24 @@ static int run_plan(b200ad_unet* h, const float* x, const float* t, const float*
         break;
       case OP_ATTN:
         CK(launch_attention(op.src, op.dst, h->N, op.C, op.H, op.W, st));
+        ++launches;
+        break;
+      case OP_LN:
+        CK(launch_layernorm_pf8(op.src, op.dst, op.fw, op.fb, h->N, op.C, op.H, op.W, op.eps, st));
+        ++launches;
+        break;
+      case OP_GEGLU:
+        CK(launch_geglu_pf8(op.src, op.dst, h->N, op.C, op.H, op.W, st));
+        ++launches;
+        break;
+      case OP_MHA:
+        CK(launch_mha_flash(op.src, op.dst, h->N, op.C, op.cin, op.H, op.W, st));
+        ++launches;
+        break;
+      case OP_XVEC:
+        if (!h->enc) return set_err("conditional U-Net: call b200ad_unet_set_encoding before forward");
+        if (h->enc_S != 1) return set_err("conditional U-Net: encoder sequence length %d (only 1 is implemented)", h->enc_S);
+        CK(launch_cross_attn_vec(h->enc, op.fw, op.fb, op.fc, op.f1, h->N, op.C, op.cin, st));
         ++launches;
         break;
       case OP_CONV_OUT: {
@@ -491,6 +472,14 @@ extern "C" int b200ad_unet_profile_step(b200ad_unet* h, const float* x, const fl
   }
   for (auto& e : ev) cudaEventDestroy(e);
   return nops;
+}
+
+extern "C" int b200ad_unet_set_encoding(b200ad_unet* h, const float* enc, int S) {
+  if (!h->cfg.cross_attention_dim) return set_err("set_encoding: this U-Net is unconditional");
+  if (S < 1) return set_err("set_encoding: empty encoder sequence");
+  h->enc = enc;
+  h->enc_S = S;
+  return 0;
 }
 
 extern "C" int b200ad_unet_forward(b200ad_unet* h, const float* x, const float* t, float* eps_out, void* stream) {

@@ -614,6 +614,7 @@ void release_backward(b200ad_unet* h) {
 // ================================================================================= C ABI
 extern "C" int b200ad_unet_set_training(b200ad_unet* h, int on) {
   if (!h) return set_err("null handle");
+  if (on && h->cfg.cross_attention_dim) return set_err("training of the conditional U-Net is not implemented (inference only)");
   if (h->training != (on != 0)) {
     h->training = on != 0;
     h->plan.clear();          // the workspace layout changes: bind_workspace must be called again

@@ -305,6 +305,7 @@ static int vae_build_plan(b200ad_vae* h, uint8_t* ws_base, int N, int H, int W, 
       op.kind = OP_CONV_OUT;
       ConvOutParams& p = op.co;
       p.src = x.p; p.stats = x.stats;
+      p.ss = B.gn_attach(x, "decoder.conv_norm_out");
       p.gamma = B.P("decoder.conv_norm_out.weight"); p.beta = B.P("decoder.conv_norm_out.bias");
       p.w = B.P("decoder.conv_out.weight"); p.b = B.P("decoder.conv_out.bias");
       p.N = N; p.C = x.C; p.H = hh; p.W = ww; p.cout = c.out_channels; p.groups = c.norm_num_groups; p.eps = c.norm_eps;

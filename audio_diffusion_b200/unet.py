@@ -136,6 +136,10 @@ class UNet2DModel(nn.Module):
             c.up_attn[i] = 1 if up_block_types[i] == "AttnUpBlock2D" else 0
         c.norm_num_groups, c.norm_eps = norm_num_groups, norm_eps
         c.attention_head_dim = attention_head_dim if attention_head_dim is not None else -1
+        self._init_engine(c, seed)
+
+    def _init_engine(self, c: UNetConfigC, seed: Optional[int]) -> None:
+        """Create the library handle and the fp32 master parameters (table and naming come from the library)."""
         self._c = c
         L = _lib.lib()
         h = C.c_void_p()
@@ -153,7 +157,8 @@ class UNet2DModel(nn.Module):
             self._pnames.append(name)
         for name in self._pnames:
             shape = shapes[name]
-            is_norm = (".norm" in name) or ("group_norm" in name) or name.startswith("conv_norm_out")
+            leaf = name.rsplit(".", 2)[-2]
+            is_norm = leaf.startswith("norm") or leaf == "group_norm" or leaf == "conv_norm_out"
             if is_norm:
                 t = torch.ones(shape) if name.endswith(".weight") else torch.zeros(shape)
             else:
@@ -165,6 +170,7 @@ class UNet2DModel(nn.Module):
         self._packed_key = None
         self._ws = None
         self._ws_key = None
+        self._plist = None
 
     # ------------------------------------------------------------------ diffusers ModelMixin persistence
     @classmethod
@@ -198,8 +204,10 @@ class UNet2DModel(nn.Module):
     def _ensure_bound(self, n: int, hh: int, ww: int) -> None:
         _lib.require_cuda()
         L = _lib.lib()
-        named = self._named()
-        params = [named[k] for k in self._pnames]
+        if self._plist is None:            # Parameter objects are stable (module.to() swaps .data); resolve the names once
+            named = self._named()
+            self._plist = [named[k] for k in self._pnames]
+        params = self._plist
         dev = params[0].device
         if dev.type != "cuda":
             raise _lib.B200ADError("UNet2DModel(b200): parameters must live on a CUDA device (call .to('cuda'))")

@@ -33,7 +33,12 @@ typedef struct {
   int up_attn[B200AD_MAX_BLOCKS];     /* 1 where up_block_types[i] == "AttnUpBlock2D"                    */
   int norm_num_groups;                /* 32                                                              */
   float norm_eps;                     /* 1e-5                                                            */
-  int attention_head_dim;             /* 8 (only 8 is implemented)                                       */
+  int attention_head_dim;             /* UNet2DModel: 8 (only 8 is implemented).  Conditional model: diffusers uses
+                                         this number as the HEAD COUNT (8): head_dim = channels / 8            */
+  /* UNet2DConditionModel as built at scripts/train_unet.py:139-159 (all zero for UNet2DModel):              */
+  int cross_attention_dim;            /* width of the audio encoding (100); 0 = unconditional UNet2DModel   */
+  int down_cross[B200AD_MAX_BLOCKS];  /* 1 where down_block_types[i] == "CrossAttnDownBlock2D"               */
+  int up_cross[B200AD_MAX_BLOCKS];    /* 1 where up_block_types[i] == "CrossAttnUpBlock2D"                   */
 } b200ad_unet_config;
 
 typedef struct b200ad_unet b200ad_unet;
@@ -61,6 +66,10 @@ int b200ad_unet_bind_workspace(b200ad_unet* h, void* workspace, size_t bytes, in
 /* model_output = unet(sample, timestep)["sample"]   (pipeline_audio_diffusion.py:163, :237).
  * x, eps_out: fp32 NCHW [N, in/out_channels, H, W]; t: float[N] timesteps (device). */
 int b200ad_unet_forward(b200ad_unet* h, const float* x, const float* t, float* eps_out, void* stream);
+
+/* Conditional model only: encoder_hidden_states of the next forward (pipeline_audio_diffusion.py:160-161),
+ * fp32 [N][S][cross_attention_dim] on the device; S = 1 (what audiodiffusion/audio_encoder.py produces) is implemented. */
+int b200ad_unet_set_encoding(b200ad_unet* h, const float* enc, int S);
 
 /* Scheduler-update coefficients (host scalars, computed exactly as DDPMScheduler.step / DDIMScheduler.step do,
  * pipeline_audio_diffusion.py:165-179):

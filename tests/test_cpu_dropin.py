@@ -328,3 +328,38 @@ print('ok')
 """
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not present (GPU box)")
+def test_reference_audio_encoder_and_conditional_unet_surface():
+    """SURVEY §8 f3 boundary: the reference's own audiodiffusion/audio_encoder.py runs on the shim's ModelMixin / Mel (a
+    small CNN that is not part of the denoising loop), and `diffusers.UNet2DConditionModel` resolves to the engine's class
+    with exactly the diffusers state-dict keys / shapes of the architecture scripts/train_unet.py:139-159 builds."""
+    code = f"""
+import sys, tempfile
+sys.path[:0] = [{ROOT!r}, {os.path.join(ROOT, 'audio_diffusion_b200', 'compat')!r}, {REF!r}]
+import torch
+from audiodiffusion.audio_encoder import AudioEncoder          # byte-identical reference file
+enc = AudioEncoder().eval()
+y = enc(torch.rand(2, 1, 96, 216))
+assert y.shape == (2, 100)
+d = tempfile.mkdtemp()
+enc.save_pretrained(d)
+again = AudioEncoder.from_pretrained(d).eval()
+assert torch.equal(again(torch.ones(1, 1, 96, 216)), enc(torch.ones(1, 1, 96, 216)))
+from diffusers import UNet2DConditionModel
+from audiodiffusion.pipeline_audio_diffusion import UNet2DConditionModel as seen_by_pipeline
+assert seen_by_pipeline is UNet2DConditionModel
+u = UNet2DConditionModel(sample_size=(32, 32), in_channels=1, out_channels=1, layers_per_block=2,
+                         block_out_channels=(128, 256, 512, 512),
+                         down_block_types=("CrossAttnDownBlock2D",) * 3 + ("DownBlock2D",),
+                         up_block_types=("UpBlock2D",) + ("CrossAttnUpBlock2D",) * 3, cross_attention_dim=100)
+from oracle.unet_cond_oracle import CondUNetConfig, param_shapes
+sh = param_shapes(CondUNetConfig(sample_size=(32, 32)))
+sd = u.state_dict()
+assert set(sh) == set(sd) and all(tuple(sd[k].shape) == tuple(sh[k]) for k in sh)
+assert sum(v.numel() for v in sd.values()) == 135559809
+print('ok')
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]

@@ -131,11 +131,19 @@ def test_full_trajectory_reference_arch_64(cuda, kind, steps):
     if kind == "ddpm":
         assert d.mean() <= 1.0 and (d <= 2).mean() >= 0.99
     else:
-        # sensitivity of the reference trajectory itself: same oracle, initial noise rounded to bf16
+        # sensitivity of the reference trajectory itself: same oracle, (1) initial noise rounded to bf16, (2) the sample rounded
+        # to bf16 after every step (one 2^-9 perturbation per step instead of one per layer and step as on the device)
         pert = _oracle_trajectory(w, ocfg, osch, noise.to(torch.bfloat16).to(torch.float32), steps, None, eta=0.0)
-        ds = np.abs(_u8(pert).astype(int) - _u8(ref).astype(int))
-        print(f"ddim-{steps} oracle self-drift under a bf16-rounded start: mean |d| {ds.mean():.3f}, within 8: {(ds <= 8).mean():.3f}")
-        assert d.mean() <= 1.5 * ds.mean() + 1.0
+        ds1 = np.abs(_u8(pert).astype(int) - _u8(ref).astype(int)).mean()
+        from oracle.unet_oracle import unet_forward
+        osch.set_timesteps(steps)
+        x = noise.clone()
+        with torch.no_grad():
+            for t in osch.timesteps:
+                x = osch.step(unet_forward(w, ocfg, x, t), t, x, eta=0.0)["prev_sample"].to(torch.bfloat16).to(torch.float32)
+        ds2 = np.abs(_u8(x).astype(int) - _u8(ref).astype(int)).mean()
+        print(f"ddim-{steps} oracle self-drift: bf16-rounded start {ds1:.3f}, bf16-rounded sample every step {ds2:.3f} grey levels")
+        assert d.mean() <= 2.0 * max(ds1, ds2) + 1.0
 
 
 class _FrozenMel:
