@@ -27,67 +27,84 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 //   S1[n][c] = sum_pix gy, S2[n][c] = sum_pix gy * xhat;  dbeta = sum_n S1, dgamma = sum_n S2
 //   gx = rstd * (gamma * gy - (A + xhat * B) / M),  A = sum_{c in group} gamma_c S1_c, B = sum gamma_c S2_c, M = cpg*H*W
 constexpr int GB_THREADS = 256;
-constexpr int GB_PIX = 4096;   // pixels per CTA in the reduction pass
+constexpr int GB_PIX = 4096;     // pixels per CTA in chan_sum
+constexpr int GB_CHUNK = 8192;   // flat PF8 positions per CTA of the GroupNorm passes (32 vectors per thread, 4 in flight)
 
-__device__ __forceinline__ void group_stats(const GnBwdParams& p, int n, float* gmean, float* grstd) {
+// Both passes walk the FLAT position range [0, H * Wp) of one 8-channel plane (coalesced 16-byte vectors, no div / mod per
+// pixel).  The pad column of every row is zero in the raw tensors AND in the incoming gradient (conv_tc_kernel writes the
+// layout's guards as zeros), so it contributes nothing to the sums; the apply pass writes zeros there.
+// A CTA only needs the statistics of the (at most two) groups its plane touches: eight threads derive them.
+struct PlaneCoef {
+  float mean[8], rstd[8], gam[8], bet[8];
+};
+__device__ __forceinline__ void plane_coef(const GnBwdParams& p, int n, int pl, float (*sm)[8], PlaneCoef& k) {
   const int Ct = p.C[0] + p.C[1];
   const int cpg = Ct / p.groups;
-  for (int gi = threadIdx.x; gi < p.groups; gi += blockDim.x) {
+  if (threadIdx.x < 8) {
+    const int c = pl * 8 + threadIdx.x, gi = c / cpg;
     double s = 0., q = 0.;
-    for (int c = gi * cpg; c < (gi + 1) * cpg; c += 4) {
-      const stat_t* st = (c < p.C[0]) ? p.stats[0] + ((long long)n * (p.C[0] >> 2) + (c >> 2)) * 2
-                                     : p.stats[1] + ((long long)n * (p.C[1] >> 2) + ((c - p.C[0]) >> 2)) * 2;
+    for (int cc = gi * cpg; cc < (gi + 1) * cpg; cc += 4) {
+      const stat_t* st = (cc < p.C[0]) ? p.stats[0] + ((long long)n * (p.C[0] >> 2) + (cc >> 2)) * 2
+                                      : p.stats[1] + ((long long)n * (p.C[1] >> 2) + ((cc - p.C[0]) >> 2)) * 2;
       s += st[0];
       q += st[1];
     }
     const double cnt = (double)cpg * (double)p.H * (double)p.W;
     const double mean = s / cnt;
-    gmean[gi] = (float)mean;
-    grstd[gi] = (float)(1.0 / sqrt(fmax(q / cnt - mean * mean, 0.) + (double)p.eps));
+    sm[0][threadIdx.x] = (float)mean;
+    sm[1][threadIdx.x] = (float)(1.0 / sqrt(fmax(q / cnt - mean * mean, 0.) + (double)p.eps));
+    sm[2][threadIdx.x] = p.gamma[c];
+    sm[3][threadIdx.x] = p.beta[c];
   }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { k.mean[e] = sm[0][e]; k.rstd[e] = sm[1][e]; k.gam[e] = sm[2][e]; k.bet[e] = sm[3][e]; }
 }
 
+// silu'(y) = s (1 + y (1 - s)), s = sigmoid(y) = 0.5 + 0.5 tanh(y / 2): one MUFU per element
 __device__ __forceinline__ float silu_grad(float y) {
-  const float sig = 1.0f / (1.0f + __expf(-y));
-  return sig * (1.0f + y * (1.0f - sig));
+  const float sig = fmaf(0.5f, tanh_approx(0.5f * y), 0.5f);
+  return sig * fmaf(y, 1.0f - sig, 1.0f);
 }
 
-// pass 1: grid (pixel chunks, planes, N). Thread-local sums over the CTA's pixels of one 8-channel plane.
-__global__ void __launch_bounds__(GB_THREADS) gn_bwd_reduce_kernel(const GnBwdParams p) {
-  __shared__ float gmean[64], grstd[64];
+// pass 1: grid (position chunks, planes, N). Thread-local sums over the CTA's positions of one 8-channel plane.
+__global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_reduce_kernel(const GnBwdParams p) {
+  __shared__ float coef[4][8];
   __shared__ float red[GB_THREADS / 32][16];
   const int Ct = p.C[0] + p.C[1];
   const int n = blockIdx.z, pl = blockIdx.y;
-  const int cpg = Ct / p.groups;
   const Geom g = make_geom(p.N, p.H, p.W);
-  group_stats(p, n, gmean, grstd);
-  __syncthreads();
+  PlaneCoef k;
+  plane_coef(p, n, pl, coef, k);
   const int planes0 = p.C[0] >> 3;
   const __nv_bfloat16* xs = (pl < planes0) ? p.src[0] + ((long long)n * planes0 + pl) * g.PL * 8
                                           : p.src[1] + ((long long)n * (p.C[1] >> 3) + (pl - planes0)) * g.PL * 8;
   const __nv_bfloat16* gs = p.ga + ((long long)n * (Ct >> 3) + pl) * g.PL * 8;
-  float mean[8], rstd[8], gam[8], bet[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int c = pl * 8 + e, gi = c / cpg;
-    mean[e] = gmean[gi]; rstd[e] = grstd[gi]; gam[e] = p.gamma[c]; bet[e] = p.beta[c];
-  }
+  const uint4* xv4 = reinterpret_cast<const uint4*>(xs) + g.lead;
+  const uint4* gv4 = reinterpret_cast<const uint4*>(gs) + g.lead;
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const int hw = p.H * p.W;
-  const int pend = min(hw, (int)(blockIdx.x + 1) * GB_PIX);
-  for (int pidx = blockIdx.x * GB_PIX + threadIdx.x; pidx < pend; pidx += GB_THREADS) {
-    const int h = pidx / p.W, w = pidx - h * p.W;
-    const long long pix = (long long)(g.lead + h * g.Wp + w) * 8;
-    float xv[8], gv[8];
-    unpack8(*reinterpret_cast<const uint4*>(xs + pix), xv);
-    unpack8(*reinterpret_cast<const uint4*>(gs + pix), gv);
+  const int mend = min(p.H * g.Wp, (int)(blockIdx.x + 1) * GB_CHUNK);
+  for (int m0 = blockIdx.x * GB_CHUNK + threadIdx.x; m0 < mend; m0 += 4 * GB_THREADS) {
+    uint4 xr[4], gr[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float xh = (xv[e] - mean[e]) * rstd[e];
-      float gy = gv[e];
-      if (p.silu) gy *= silu_grad(gam[e] * xh + bet[e]);
-      s1[e] += gy;
-      s2[e] = fmaf(gy, xh, s2[e]);
+    for (int u = 0; u < 4; ++u) {
+      const int m = m0 + u * GB_THREADS;
+      if (m < mend) { xr[u] = xv4[m]; gr[u] = gv4[m]; }
+      else { xr[u] = make_uint4(0, 0, 0, 0); gr[u] = make_uint4(0, 0, 0, 0); }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float xv[8], gv[8];
+      unpack8(xr[u], xv);
+      unpack8(gr[u], gv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xh = (xv[e] - k.mean[e]) * k.rstd[e];
+        float gy = gv[e];
+        if (p.silu) gy *= silu_grad(fmaf(k.gam[e], xh, k.bet[e]));
+        s1[e] += gy;
+        s2[e] = fmaf(gy, xh, s2[e]);
+      }
     }
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -99,66 +116,84 @@ __global__ void __launch_bounds__(GB_THREADS) gn_bwd_reduce_kernel(const GnBwdPa
   __syncthreads();
   if (threadIdx.x < 16) {
     float t = 0.f;
-    for (int k = 0; k < GB_THREADS / 32; ++k) t += red[k][threadIdx.x];
+    for (int w = 0; w < GB_THREADS / 32; ++w) t += red[w][threadIdx.x];
     const int e = threadIdx.x & 7, which = threadIdx.x >> 3;
     atomicAdd(p.sums + ((long long)n * Ct + pl * 8 + e) * 2 + which, t);
     if (p.dgamma) atomicAdd((which ? p.dgamma : p.dbeta) + pl * 8 + e, t);   // dbeta = sum S1, dgamma = sum S2 over n
   }
 }
 
-// pass 2: grid (pixel chunks of 256, planes, N): gx (+ optional addends) for one pixel x one plane per thread
-__global__ void __launch_bounds__(GB_THREADS) gn_bwd_apply_kernel(const GnBwdParams p) {
-  __shared__ float gmean[64], grstd[64], gA[64], gB[64];
+// pass 2: grid (position chunks, planes, N): gx (+ optional addends) of one plane
+__global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_apply_kernel(const GnBwdParams p) {
+  __shared__ float coef[4][8];
+  __shared__ float gAB[2][8];
   const int Ct = p.C[0] + p.C[1];
   const int n = blockIdx.z, pl = blockIdx.y;
   const int cpg = Ct / p.groups;
   const Geom g = make_geom(p.N, p.H, p.W);
-  group_stats(p, n, gmean, grstd);
-  const float invM = 1.0f / ((float)cpg * (float)p.H * (float)p.W);
-  for (int gi = threadIdx.x; gi < p.groups; gi += blockDim.x) {
+  if (threadIdx.x >= 32 && threadIdx.x < 40) {   // (A, B) / M of this channel's group (a second warp, next to plane_coef's)
+    const int e = threadIdx.x - 32, c = pl * 8 + e, gi = c / cpg;
     float a = 0.f, b = 0.f;
-    for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
-      a = fmaf(p.gamma[c], p.sums[((long long)n * Ct + c) * 2], a);
-      b = fmaf(p.gamma[c], p.sums[((long long)n * Ct + c) * 2 + 1], b);
+    for (int cc = gi * cpg; cc < (gi + 1) * cpg; ++cc) {
+      const float gm = p.gamma[cc];
+      a = fmaf(gm, p.sums[((long long)n * Ct + cc) * 2], a);
+      b = fmaf(gm, p.sums[((long long)n * Ct + cc) * 2 + 1], b);
     }
-    gA[gi] = a * invM;
-    gB[gi] = b * invM;
+    const float invM = 1.0f / ((float)cpg * (float)p.H * (float)p.W);
+    gAB[0][e] = a * invM;
+    gAB[1][e] = b * invM;
   }
-  __syncthreads();
-  const int pidx = blockIdx.x * GB_THREADS + threadIdx.x;
-  if (pidx >= p.H * p.W) return;
-  const int h = pidx / p.W, w = pidx - h * p.W;
-  const long long pix = (long long)(g.lead + h * g.Wp + w) * 8;
+  PlaneCoef k;
+  plane_coef(p, n, pl, coef, k);
+  float gA[8], gB[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { gA[e] = gAB[0][e]; gB[e] = gAB[1][e]; }
   const int planes0 = p.C[0] >> 3;
   const bool first = pl < planes0;
   const int lp = first ? pl : pl - planes0;                 // plane inside its own source / destination
   const int lplanes = first ? planes0 : (p.C[1] >> 3);
-  const __nv_bfloat16* xs = (first ? p.src[0] : p.src[1]) + ((long long)n * lplanes + lp) * g.PL * 8;
-  float xv[8], gv[8], o[8];
-  unpack8(*reinterpret_cast<const uint4*>(xs + pix), xv);
-  unpack8(*reinterpret_cast<const uint4*>(p.ga + ((long long)n * (Ct >> 3) + pl) * g.PL * 8 + pix), gv);
+  const uint4* xv4 = reinterpret_cast<const uint4*>((first ? p.src[0] : p.src[1]) + ((long long)n * lplanes + lp) * g.PL * 8) + g.lead;
+  const uint4* gv4 = reinterpret_cast<const uint4*>(p.ga + ((long long)n * (Ct >> 3) + pl) * g.PL * 8) + g.lead;
+  const uint4* as4 = p.addS ? reinterpret_cast<const uint4*>(p.addS + ((long long)n * (Ct >> 3) + pl) * g.PL * 8) + g.lead : nullptr;
+  const uint4* a04 = (p.add0 && first) ? reinterpret_cast<const uint4*>(p.add0 + ((long long)n * planes0 + pl) * g.PL * 8) + g.lead : nullptr;
+  uint4* dv4 = reinterpret_cast<uint4*>((first ? p.dst[0] : p.dst[1]) + ((long long)n * lplanes + lp) * g.PL * 8) + g.lead;
+  const int mend = min(p.H * g.Wp, (int)(blockIdx.x + 1) * GB_CHUNK);
+  int m0 = blockIdx.x * GB_CHUNK + threadIdx.x;
+  int col = m0 % g.Wp;
+  const int dcol = GB_THREADS % g.Wp;
+  for (; m0 < mend; m0 += 4 * GB_THREADS) {
+    uint4 xr[4], gr[4], ar[4], br[4];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int c = pl * 8 + e, gi = c / cpg;
-    const float rs = grstd[gi], xh = (xv[e] - gmean[gi]) * rs, gam = p.gamma[c];
-    float gy = gv[e];
-    if (p.silu) gy *= silu_grad(gam * xh + p.beta[c]);
-    o[e] = rs * (gam * gy - (gA[gi] + xh * gB[gi]));
-  }
-  if (p.addS) {
-    float av[8];
-    unpack8(*reinterpret_cast<const uint4*>(p.addS + ((long long)n * (Ct >> 3) + pl) * g.PL * 8 + pix), av);
+    for (int u = 0; u < 4; ++u) {
+      const int m = m0 + u * GB_THREADS;
+      const bool in = m < mend;
+      xr[u] = in ? xv4[m] : make_uint4(0, 0, 0, 0);
+      gr[u] = in ? gv4[m] : make_uint4(0, 0, 0, 0);
+      ar[u] = (in && as4) ? as4[m] : make_uint4(0, 0, 0, 0);
+      br[u] = (in && a04) ? a04[m] : make_uint4(0, 0, 0, 0);
+    }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] += av[e];
-  }
-  if (p.add0 && first) {
-    float av[8];
-    unpack8(*reinterpret_cast<const uint4*>(p.add0 + ((long long)n * planes0 + pl) * g.PL * 8 + pix), av);
+    for (int u = 0; u < 4; ++u) {
+      const int m = m0 + u * GB_THREADS;
+      const bool pad = col == p.W;
+      col += dcol;
+      if (col >= g.Wp) col -= g.Wp;
+      if (m >= mend) continue;
+      float xv[8], gv[8], av[8], bv[8], o[8];
+      unpack8(xr[u], xv);
+      unpack8(gr[u], gv);
+      unpack8(ar[u], av);
+      unpack8(br[u], bv);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] += av[e];
+      for (int e = 0; e < 8; ++e) {
+        const float xh = (xv[e] - k.mean[e]) * k.rstd[e];
+        float gy = gv[e];
+        if (p.silu) gy *= silu_grad(fmaf(k.gam[e], xh, k.bet[e]));
+        o[e] = k.rstd[e] * (k.gam[e] * gy - (gA[e] + xh * gB[e])) + av[e] + bv[e];
+      }
+      dv4[m] = pad ? make_uint4(0, 0, 0, 0) : pack8(o);
+    }
   }
-  __nv_bfloat16* dp = (first ? p.dst[0] : p.dst[1]) + ((long long)n * lplanes + lp) * g.PL * 8;
-  *reinterpret_cast<uint4*>(dp + pix) = pack8(o);
 }
 
 cudaError_t launch_gn_bwd(const GnBwdParams& p, cudaStream_t s) {
@@ -166,10 +201,11 @@ cudaError_t launch_gn_bwd(const GnBwdParams& p, cudaStream_t s) {
   if (p.groups > 64 || (Ct % p.groups)) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(p.sums, 0, (size_t)p.N * Ct * 2 * sizeof(float), s);
   if (e != cudaSuccess) return e;
-  const int hw = p.H * p.W;
-  gn_bwd_reduce_kernel<<<dim3((hw + GB_PIX - 1) / GB_PIX, Ct >> 3, p.N), GB_THREADS, 0, s>>>(p);
+  const int npos = p.H * (p.W + 1);
+  const dim3 grid((npos + GB_CHUNK - 1) / GB_CHUNK, Ct >> 3, p.N);
+  gn_bwd_reduce_kernel<<<grid, GB_THREADS, 0, s>>>(p);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  gn_bwd_apply_kernel<<<dim3((hw + GB_THREADS - 1) / GB_THREADS, Ct >> 3, p.N), GB_THREADS, 0, s>>>(p);
+  gn_bwd_apply_kernel<<<grid, GB_THREADS, 0, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -40,8 +40,14 @@ namespace b200ad {
 constexpr int CONV_THREADS = 512;     // 16 warps
 constexpr int CONV_XF_THREADS = 160;  // transform warps 2, 8, 9, 10, 11
 constexpr int CONV_HALF = 2 * CONV_TM;      // pixels per epilogue half (256 accumulator columns)
+#ifdef CONV_STG_HALF   // round-2 first version: ONE staging buffer of a half item (the second half waits for the first half's store)
 constexpr int CONV_SPLANE = CONV_HALF * 16 + 32;  // epilogue staging: bytes per 8-channel plane (256 pixels x 16 B, +32 B bank skew)
 constexpr int CONV_STAGING = 16 * CONV_SPLANE;    // one half item: 16 planes (128 channels) x 256 pixels, bf16
+#else                  // two buffers of one 128-pixel tile each: the store of tile s drains while tile s+1 is converted
+constexpr int CONV_SPLANE = CONV_TM * 16 + 32;    // bytes per 8-channel plane of a buffer (128 pixels x 16 B, +32 B bank skew)
+constexpr int CONV_STG_BUF = 16 * CONV_SPLANE;    // one tile: 16 planes (128 channels) x 128 pixels, bf16
+constexpr int CONV_STAGING = 2 * CONV_STG_BUF;
+#endif
 
 struct WorkItem {
   int n, ntile, m0, G;
@@ -97,9 +103,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
   const uint32_t bar_emptyA = smem_u32(bars + 2 * AS);
   const uint32_t bar_fullB = smem_u32(bars + 3 * AS);
   const uint32_t bar_emptyB = smem_u32(bars + 3 * AS + BS);
-  const uint32_t bar_tfull = smem_u32(bars + 3 * AS + 2 * BS);
-  const uint32_t bar_tempty = smem_u32(bars + 3 * AS + 2 * BS + 1);
-  static_assert((3 * AS + 2 * BS + 2) * 8 <= 504, "barrier block overflows");
+  const uint32_t bar_tfull = smem_u32(bars + 3 * AS + 2 * BS);        // [2]: accumulator half h is complete
+  const uint32_t bar_tempty = smem_u32(bars + 3 * AS + 2 * BS + 2);   // [2]: accumulator half h has been read out
+  static_assert((3 * AS + 2 * BS + 4) * 8 <= 504, "barrier block overflows");
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < AS; ++s) {
@@ -111,8 +117,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
       mbar_init(bar_fullB + 8 * s, 1);
       mbar_init(bar_emptyB + 8 * s, 1);
     }
-    mbar_init(bar_tfull, 1);
-    mbar_init(bar_tempty, 256);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(bar_tfull + 8 * h, 1);
+      mbar_init(bar_tempty + 8 * h, 256);
+    }
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -195,45 +203,91 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
       const int n0 = min(wi.G, 2) * CONV_TM, n1 = (wi.G - 2) * CONV_TM;
       const uint32_t idesc0 = (n0 == 256) ? idesc256 : make_idesc_bf16(CONV_NT, CONV_TM);
       const uint32_t idesc1 = (n1 == 256) ? idesc256 : make_idesc_bf16(CONV_NT, CONV_TM);
-      mbar_wait_warp(bar_tempty, (item & 1) ^ 1);  // the epilogue has moved the previous item out of TMEM
-      tc_fence_after();
-      uint32_t fresh = 1;  // first k-step of the item overwrites the accumulators
+      const bool two = n1 > 0 && !(p.dbg & 16);   // both accumulator halves in use: split the boundary k-steps
+      const uint32_t epar = (item & 1) ^ 1;
+      if (!two) {  // the epilogue has moved the previous item out of TMEM
+        mbar_wait_warp(bar_tempty, epar);
+        mbar_wait_warp(bar_tempty + 8, epar);
+        tc_fence_after();
+      }
+      int kidx = 0;
       for (int s = 0; s < p.nseg; ++s) {
         const ConvSeg& sg = p.seg[s];
         const int npix = wi.G * CONV_TM + (sg.ht + sg.hb) * p.Wp + sg.hl + sg.hr;
         const uint32_t xdesc_lo_hi = ((uint32_t)npix & 0x3FFF) << 16;  // LBO of the pixel windows = npix * 16 B
         const int ntaps = sg.ntaps;
-        for (int ks = 0; ks < sg.ksteps; ++ks) {
+        for (int ks = 0; ks < sg.ksteps; ++ks, ++kidx) {
+          const bool first = kidx == 0, last = kidx == p.ktotal - 1;
           mbar_wait_warp(bar_readyA + 8 * sa, pa);   // windows landed and (if asked) normalised in place
           const uint32_t abase16 = (smem_base + sa * a_bytes) >> 4;
-          for (int t0 = 0; t0 < ntaps; t0 += CONV_BT) {
-            mbar_wait_warp(bar_fullB + 8 * sb, pb);  // this slot's taps landed
-            tc_fence_after();
-            const uint32_t bbase16 = (bring_base + sb * CONV_B_SLOT) >> 4;
-            const int nt = min(CONV_BT, ntaps - t0);
-            if (elect_one()) {
-              for (int t = 0; t < nt; ++t) {
-                const uint64_t wdesc = desc_hi | (uint64_t)((bbase16 + (uint32_t)t * (CONV_B_TAP >> 4)) | wdesc_lo_hi);
-                const uint32_t x_lo = (abase16 + (uint32_t)sg.aoff[t0 + t]) | xdesc_lo_hi;
-                const uint32_t accum = (fresh && t0 + t == 0) ? 0u : 1u;
-                if (n1 > 0) {  // two pixel groups share the weights: latch them in the A collector
-                  umma_bf16_afill(d0, wdesc, desc_hi | (uint64_t)x_lo, idesc0, accum);
-                  umma_bf16_alast(d0 + CONV_HALF, wdesc, desc_hi | (uint64_t)(x_lo + (CONV_HALF * 16 >> 4)), idesc1, accum);
-                } else {
-                  umma_bf16(d0, wdesc, desc_hi | (uint64_t)x_lo, idesc0, accum);
+          if (two && (first || last)) {
+            // Boundary k-step, half by half: all taps into columns 0-255, then all taps into 256-511 (the weights are read
+            // from shared memory twice instead of being latched).  Half 0 of the LAST k-step is complete one k-step's worth
+            // of MMAs before half 1, and half 0 of the next item's FIRST k-step only needs half 0 drained: the epilogue of
+            // either half runs under the other half's MMAs.
+            const int sb0 = sb;
+            const uint32_t pb0 = pb;
+            for (int h = 0; h < 2; ++h) {
+              if (first) {
+                mbar_wait_warp(bar_tempty + 8 * h, epar);
+                tc_fence_after();
+              }
+              sb = sb0; pb = pb0;
+              const uint32_t dh = d0 + (uint32_t)(h * CONV_HALF);
+              const uint32_t xoff = (uint32_t)(h * (CONV_HALF * 16 >> 4));
+              const uint32_t idesc = h ? idesc1 : idesc0;
+              for (int t0 = 0; t0 < ntaps; t0 += CONV_BT) {
+                if (h == 0) {
+                  mbar_wait_warp(bar_fullB + 8 * sb, pb);  // this slot's taps landed (still resident in the second pass)
+                  tc_fence_after();
+                }
+                const uint32_t bbase16 = (bring_base + sb * CONV_B_SLOT) >> 4;
+                const int nt = min(CONV_BT, ntaps - t0);
+                if (elect_one()) {
+                  for (int t = 0; t < nt; ++t) {
+                    const uint64_t wdesc = desc_hi | (uint64_t)((bbase16 + (uint32_t)t * (CONV_B_TAP >> 4)) | wdesc_lo_hi);
+                    const uint32_t x_lo = (abase16 + (uint32_t)sg.aoff[t0 + t] + xoff) | xdesc_lo_hi;
+                    umma_bf16(dh, wdesc, desc_hi | (uint64_t)x_lo, idesc, (first && t0 + t == 0) ? 0u : 1u);
+                  }
+                }
+                __syncwarp();
+                if (h == 1) umma_commit_elect(bar_emptyB + 8 * sb);  // frees the weight slot when these MMAs retire
+                if (++sb == BS) { sb = 0; pb ^= 1; }
+              }
+              if (last) umma_commit_elect(bar_tfull + 8 * h);
+            }
+          } else {
+            for (int t0 = 0; t0 < ntaps; t0 += CONV_BT) {
+              mbar_wait_warp(bar_fullB + 8 * sb, pb);  // this slot's taps landed
+              tc_fence_after();
+              const uint32_t bbase16 = (bring_base + sb * CONV_B_SLOT) >> 4;
+              const int nt = min(CONV_BT, ntaps - t0);
+              if (elect_one()) {
+                for (int t = 0; t < nt; ++t) {
+                  const uint64_t wdesc = desc_hi | (uint64_t)((bbase16 + (uint32_t)t * (CONV_B_TAP >> 4)) | wdesc_lo_hi);
+                  const uint32_t x_lo = (abase16 + (uint32_t)sg.aoff[t0 + t]) | xdesc_lo_hi;
+                  const uint32_t accum = (first && t0 + t == 0) ? 0u : 1u;
+                  if (n1 > 0) {  // two pixel groups share the weights: latch them in the A collector
+                    umma_bf16_afill(d0, wdesc, desc_hi | (uint64_t)x_lo, idesc0, accum);
+                    umma_bf16_alast(d0 + CONV_HALF, wdesc, desc_hi | (uint64_t)(x_lo + (CONV_HALF * 16 >> 4)), idesc1, accum);
+                  } else {
+                    umma_bf16(d0, wdesc, desc_hi | (uint64_t)x_lo, idesc0, accum);
+                  }
                 }
               }
+              __syncwarp();
+              umma_commit_elect(bar_emptyB + 8 * sb);  // frees the weight slot when these MMAs retire
+              if (++sb == BS) { sb = 0; pb ^= 1; }
             }
-            __syncwarp();
-            umma_commit_elect(bar_emptyB + 8 * sb);  // frees the weight slot when these MMAs retire
-            if (++sb == BS) { sb = 0; pb ^= 1; }
           }
-          fresh = 0;
           umma_commit_elect(bar_emptyA + 8 * sa);    // frees the activation slot
           if (++sa == AS) { sa = 0; pa ^= 1; }
         }
       }
-      umma_commit_elect(bar_tfull);
+      if (!two) {
+        umma_commit_elect(bar_tfull);
+        umma_commit_elect(bar_tfull + 8);
+      }
     }
   } else if ((warp >= 4 && warp < 8) || warp >= 12) {
     // ================================ epilogue (8 warps). TMEM lane = output channel (interleaved, conv_lane_channel),
@@ -268,7 +322,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
       const int nchunk = (p.dbg & 8) ? 0 : wi.G * (CONV_TM / 32);
       const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16);
       // one 32-pixel chunk: +bias, statistics, bf16, transposed store into the staging buffer at pixel offset `spx`
-      auto process = [&](const uint32_t (&r)[32], int jc, int spx) {
+      auto process = [&](const uint32_t (&r)[32], int jc, uint32_t boff, int spx) {
         const int mc = wi.m0 + jc * 32;
         // validity mask of the chunk's 32 pixels: pad columns and the run-off behind the image are written as ZEROS (they
         // are zero guards of the layout) and do not count for the statistics
@@ -307,7 +361,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
             pk[j] = f2_to_bf16x2(vm);
           }
         }
-        const uint32_t sa = st_addr + (uint32_t)spx * 16u;
+        const uint32_t sa = st_addr + boff + (uint32_t)spx * 16u;
 #pragma unroll
         for (int k = 0; k < 4; ++k) stmatrix_x4_trans(sa + 128u * k, pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
         if (p.up2) {   // folded upsample: scatter into the 2x tensor at this launch's parity, straight from the staging rows
@@ -324,20 +378,20 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
           __syncwarp();
         }
       };
+#ifdef CONV_STG_HALF
       const int nhalf = (wi.G > 2) ? 2 : 1;
 #pragma unroll 1
-      for (int h = 0; h < nhalf; ++h) {
-        if (!p.up2) {   // the bulk stores of the previous half must have finished READING the staging planes of this quarter
+      for (int h = 0; h < 2; ++h) {
+        const bool live = h < nhalf;   // a short item (<= 256 pixels) only uses half 0; half 1 just keeps the barrier phases
+        if (live && !p.up2) {   // the bulk stores of the previous half must have finished READING the staging planes of this quarter
           if (issuer) bulk_wait_read_all();
           __syncwarp();
           named_bar_sync(1 + q, 64);
         }
-        if (h == 0) {
-          mbar_wait(bar_tfull, item & 1);
-          tc_fence_after();
-        }
+        mbar_wait(bar_tfull + 8 * h, item & 1);   // the MMAs into this half have retired
+        tc_fence_after();
         const int jbeg = 8 * h, jend = min(nchunk, 8 * h + 8);
-        {
+        if (live) {
           // two register sets: the TMEM load of this warp's next chunk is in flight while the current one is processed;
           // with the up2 scatter every chunk reuses the warp's own 32-pixel window of the staging planes
           uint32_t ra[32], rb[32];
@@ -345,21 +399,20 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
           if (jc < jend) { tmem_ld32(tsrc + (uint32_t)(jc * 32), ra); tmem_ld_wait(); }
           while (jc < jend) {
             if (jc + 2 < jend) tmem_ld32(tsrc + (uint32_t)((jc + 2) * 32), rb);
-            process(ra, jc, p.up2 ? par * 32 : (jc - jbeg) * 32);
+            process(ra, jc, 0u, p.up2 ? par * 32 : (jc - jbeg) * 32);
             tmem_ld_wait();
             jc += 2;
             if (jc >= jend) break;
             if (jc + 2 < jend) tmem_ld32(tsrc + (uint32_t)((jc + 2) * 32), ra);
-            process(rb, jc, p.up2 ? par * 32 : (jc - jbeg) * 32);
+            process(rb, jc, 0u, p.up2 ? par * 32 : (jc - jbeg) * 32);
             tmem_ld_wait();
             jc += 2;
           }
         }
-        if (h == nhalf - 1) {   // every TMEM load of this thread has landed: the MMA warp may overwrite the accumulators
-          tc_fence_before();
-          mbar_arrive(bar_tempty);
-        }
-        if (!p.up2) {
+        // every TMEM load of this thread from this half has landed: the MMA warp may overwrite it
+        tc_fence_before();
+        mbar_arrive(bar_tempty + 8 * h);
+        if (live && !p.up2) {
           fence_proxy_async_smem();           // staging rows written through the generic proxy -> visible to the TMA engine
           named_bar_sync(1 + q, 64);
           const int npx = min(CONV_HALF, wi.G * CONV_TM - CONV_HALF * h);
@@ -370,6 +423,47 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
           }
         }
       }
+
+#else
+      // The item leaves TMEM tile by tile (128 pixels = 4 chunks; the two warps of a pair take two chunks each) through two
+      // staging buffers: while the TMA engine reads tile s out of one buffer, tile s + 1 is converted into the other one.
+      // One named barrier per tile: it publishes the tile's staging rows and, because the issuer first waits for its
+      // earlier stores to have been read, tells both warps that the other buffer is free again.
+#pragma unroll 1
+      for (int sblk = 0; sblk < CONV_MAXG; ++sblk) {
+        const int h = sblk >> 1;
+        if ((sblk & 1) == 0) {
+          mbar_wait(bar_tfull + 8 * h, item & 1);   // the MMAs into this half have retired
+          tc_fence_after();
+        }
+        const bool live = sblk < wi.G && nchunk > 0;
+        const uint32_t boff = p.up2 ? 0u : (uint32_t)((sblk & 1) * CONV_STG_BUF);
+        if (live) {
+          uint32_t ra[32], rb[32];
+          const int j0 = 4 * sblk + par;
+          tmem_ld32(tsrc + (uint32_t)(j0 * 32), ra);
+          tmem_ld32(tsrc + (uint32_t)((j0 + 2) * 32), rb);
+          tmem_ld_wait();
+          process(ra, j0, boff, par * 32);
+          process(rb, j0 + 2, boff, p.up2 ? par * 32 : (par + 2) * 32);
+        }
+        if (sblk & 1) {   // every TMEM load of this thread from this half has landed: the MMA warp may overwrite it
+          tc_fence_before();
+          mbar_arrive(bar_tempty + 8 * h);
+        }
+        if (!p.up2) {
+          if (live) fence_proxy_async_smem();   // staging rows written through the generic proxy -> visible to the TMA engine
+          if (issuer) bulk_wait_read_all();     // this thread's earlier stores (the other buffer) have been read out
+          __syncwarp();
+          named_bar_sync(1 + q, 64);
+          if (live && issuer && !(p.dbg & 2)) {
+            bulk_s2g(out_pl + (long long)lane * og.PL * 8 + (long long)(p.lead + wi.m0 + CONV_TM * sblk) * 8,
+                     stg_q + boff + (uint32_t)(lane * CONV_SPLANE), (uint32_t)CONV_TM * 16u);
+            bulk_commit();
+          }
+        }
+      }
+#endif
 
       if (do_stats) {  // quad (4-channel) partial sums: channels 4k..4k+3 of a plane sit in lanes 4 apart; fp64 atomics
         const float2 s2 = f2_unpack(ssum2), q2 = f2_unpack(ssq2);
@@ -509,16 +603,28 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
 }
 
 cudaError_t launch_conv_tc(const ConvParams& p_in, int num_sms, cudaStream_t stream) {
-  static int dbg = -1;
-  if (dbg < 0) {
-    const char* e = getenv("B200AD_CONV_DBG");
-    dbg = e ? atoi(e) : 0;
-  }
+  // timing experiments only; read on every launch so that one process can alternate settings (tools/ab_conv.py)
+  const char* dbg_env = getenv("B200AD_CONV_DBG");
+  const int dbg = dbg_env ? atoi(dbg_env) : 0;
   if (p_in.nseg < 1 || p_in.nseg > CONV_MAXSEG) return cudaErrorInvalidValue;
   ConvParams p = p_in;
   p.dbg = dbg;
   for (int s = 0; s < p.nseg; ++s)
     if (p.seg[s].wtile_stride == 0) p.seg[s].wtile_stride = (long long)p.seg[s].ksteps * p.seg[s].ntaps * (CONV_B_TAP / 2);
+  // Experiment (B200AD_CONV_DBG & 128, off by default): move trailing 1-tap segments (shortcut / residual) in front of the
+  // main segment's last k-step so that a 9-tap k-step closes the K loop and the half-by-half overlap of the epilogue gets a
+  // full k-step at both ends.  Measured slower (+0.3 ms / step, in-process A/B): the 1-tap k-steps are load-bound (a 16 KB
+  // window per 256 MMA cycles) and stall the 3-deep ring in the middle of the item instead of next to the epilogue.
+  if ((dbg & 128) && p.nseg >= 2 && p.nseg < CONV_MAXSEG && p.seg[0].ksteps >= 2 && p.seg[p.nseg - 1].ntaps < p.seg[0].ntaps) {
+    ConvSeg tail = p.seg[0];
+    const int ka = tail.ksteps - 1;
+    p.seg[0].ksteps = ka;
+    tail.ksteps = 1;
+    tail.src += (long long)ka * 2 * p.PL * 8;
+    tail.wpack += (long long)ka * tail.ntaps * (CONV_B_TAP / 2);
+    if (tail.ss) tail.ss += ka * 16;
+    p.seg[p.nseg++] = tail;
+  }
   p.ktotal = 0;
   for (int s = 0; s < p.nseg; ++s) p.ktotal += p.seg[s].ksteps;
   p.groups_per_img = (p.H * p.Wp + CONV_MAXG * CONV_TM - 1) / (CONV_MAXG * CONV_TM);
