@@ -27,7 +27,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 //   S1[n][c] = sum_pix gy, S2[n][c] = sum_pix gy * xhat;  dbeta = sum_n S1, dgamma = sum_n S2
 //   gx = rstd * (gamma * gy - (A + xhat * B) / M),  A = sum_{c in group} gamma_c S1_c, B = sum gamma_c S2_c, M = cpg*H*W
 constexpr int GB_THREADS = 256;
-constexpr int GB_PIX = 4096;     // pixels per CTA in chan_sum
+constexpr int GB_PIX = 4096;     // pixels per CTA of the scalar-conv weight gradient
 constexpr int GB_CHUNK = 8192;   // flat PF8 positions per CTA of the GroupNorm passes (32 vectors per thread, 4 in flight)
 
 // Both passes walk the FLAT position range [0, H * Wp) of one 8-channel plane (coalesced 16-byte vectors, no div / mod per
@@ -217,16 +217,24 @@ __global__ void __launch_bounds__(GB_THREADS) chan_sum_kernel(const __nv_bfloat1
   __shared__ float red[GB_THREADS / 32][8];
   const int n = blockIdx.z, pl = blockIdx.y;
   const Geom g = make_geom(N, H, W);
-  const __nv_bfloat16* sp = src + ((long long)n * img_planes + pl) * g.PL * 8;
+  // flat positions of the plane: the pad column of every row holds zeros and adds nothing
+  const uint4* sv4 = reinterpret_cast<const uint4*>(src + ((long long)n * img_planes + pl) * g.PL * 8) + g.lead;
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const int hw = H * W;
-  const int pend = min(hw, (int)(blockIdx.x + 1) * GB_PIX);
-  for (int pidx = blockIdx.x * GB_PIX + threadIdx.x; pidx < pend; pidx += GB_THREADS) {
-    const int h = pidx / W, w = pidx - h * W;
-    float v[8];
-    unpack8(*reinterpret_cast<const uint4*>(sp + (long long)(g.lead + h * g.Wp + w) * 8), v);
+  const int mend = min(H * g.Wp, (int)(blockIdx.x + 1) * GB_CHUNK);
+  for (int m0 = blockIdx.x * GB_CHUNK + threadIdx.x; m0 < mend; m0 += 4 * GB_THREADS) {
+    uint4 r[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) s[e] += v[e];
+    for (int u = 0; u < 4; ++u) {
+      const int m = m0 + u * GB_THREADS;
+      r[u] = (m < mend) ? sv4[m] : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float v[8];
+      unpack8(r[u], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] += v[e];
+    }
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -247,7 +255,7 @@ cudaError_t launch_chan_sum(const __nv_bfloat16* src, float* out, int N, int C, 
                             float* bias0, float* bias1) {
   cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * C * sizeof(float), s);
   if (e != cudaSuccess) return e;
-  chan_sum_kernel<<<dim3((H * W + GB_PIX - 1) / GB_PIX, C >> 3, N), GB_THREADS, 0, s>>>(src, out, N, C, img_planes, H, W,
+  chan_sum_kernel<<<dim3((H * (W + 1) + GB_CHUNK - 1) / GB_CHUNK, C >> 3, N), GB_THREADS, 0, s>>>(src, out, N, C, img_planes, H, W,
                                                                                           bias0, bias1);
   return cudaGetLastError();
 }

@@ -106,80 +106,81 @@ cudaError_t launch_pack_weights(const float* w, int cout, int cin_total, int KH,
 }
 
 // ------------------------------------------------------------------------------------ GroupNorm apply
-constexpr int GN_PLANES_PER_CTA = 4;
+// Materialised GroupNorm(+SiLU) (the weight-gradient kernel's activation operand in the backward pass; the forward pass
+// applies the norm inside conv_tc_kernel).  grid (position chunks, planes, N): a CTA walks a flat run of one 8-channel plane
+// (coalesced 16-byte vectors, 4 in flight per thread); eight threads derive the plane's scale / shift from the fp64 sums.
+constexpr int GN_CHUNK = 8192;
 
 __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
-  extern __shared__ float gsm[];  // scale[Ct], shift[Ct], mean[groups], rstd[groups]
+  __shared__ float coef[2][8];
   const int Ct = p.C[0] + p.C[1];
-  float* scale = gsm;
-  float* shift = gsm + Ct;
-  float* gmean = gsm + 2 * Ct;
-  float* grstd = gmean + p.groups;
-  const int n = blockIdx.z;
+  const int n = blockIdx.z, pl = blockIdx.y;
   const int cpg = Ct / p.groups;
   const Geom g = make_geom(p.N, p.H, p.W);
-  for (int gi = threadIdx.x; gi < p.groups; gi += blockDim.x) {
+  if (threadIdx.x < 8) {
+    const int c = pl * 8 + threadIdx.x, gi = c / cpg;
     double s = 0., q = 0.;
-    for (int c = gi * cpg; c < (gi + 1) * cpg; c += 4) {
-      const stat_t* st = (c < p.C[0]) ? p.stats[0] + ((long long)n * (p.C[0] >> 2) + (c >> 2)) * 2
-                                     : p.stats[1] + ((long long)n * (p.C[1] >> 2) + ((c - p.C[0]) >> 2)) * 2;
+    for (int cc = gi * cpg; cc < (gi + 1) * cpg; cc += 4) {
+      const stat_t* st = (cc < p.C[0]) ? p.stats[0] + ((long long)n * (p.C[0] >> 2) + (cc >> 2)) * 2
+                                      : p.stats[1] + ((long long)n * (p.C[1] >> 2) + ((cc - p.C[0]) >> 2)) * 2;
       s += st[0];
       q += st[1];
     }
     const double cnt = (double)cpg * (double)p.H * (double)p.W;
     const double mean = s / cnt;
-    const double var = fmax(q / cnt - mean * mean, 0.);
-    gmean[gi] = (float)mean;
-    grstd[gi] = (float)(1.0 / sqrt(var + (double)p.eps));
+    const float rstd = (float)(1.0 / sqrt(fmax(q / cnt - mean * mean, 0.) + (double)p.eps));
+    const float sc = p.gamma[c] * rstd;
+    const float hs = p.silu ? 0.5f : 1.0f;    // SiLU works on a / 2: silu(a) = h + h tanh(h), h = a / 2
+    coef[0][threadIdx.x] = sc * hs;
+    coef[1][threadIdx.x] = (p.beta[c] - (float)mean * sc) * hs;
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < Ct; c += blockDim.x) {
-    const int gi = c / cpg;
-    const float sc = p.gamma[c] * grstd[gi];
-    scale[c] = sc;
-    shift[c] = p.beta[c] - gmean[gi] * sc;
-  }
-  __syncthreads();
-
-  const int pidx = blockIdx.x * blockDim.x + threadIdx.x;  // valid-pixel index
-  if (pidx >= p.H * p.W) return;
-  const int h = pidx / p.W, w = pidx - h * p.W;
-  const long long pix = (long long)(g.lead + h * g.Wp + w) * 8;
-  const int pl0 = blockIdx.y * GN_PLANES_PER_CTA;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sc[e] = coef[0][e]; sh[e] = coef[1][e]; }
   const int planes0 = p.C[0] >> 3;
-  uint4 in[GN_PLANES_PER_CTA];
+  const __nv_bfloat16* sp = (pl < planes0) ? p.src[0] + ((long long)n * planes0 + pl) * g.PL * 8
+                                          : p.src[1] + ((long long)n * (p.C[1] >> 3) + (pl - planes0)) * g.PL * 8;
+  const uint4* xv4 = reinterpret_cast<const uint4*>(sp) + g.lead;
+  uint4* dv4 = reinterpret_cast<uint4*>(p.dst + ((long long)n * (Ct >> 3) + pl) * g.PL * 8) + g.lead;
+  const int mend = min(p.H * g.Wp, (int)(blockIdx.x + 1) * GN_CHUNK);
+  int m0 = blockIdx.x * GN_CHUNK + threadIdx.x;
+  int col = m0 % g.Wp;
+  const int dcol = 256 % g.Wp;
+  for (; m0 < mend; m0 += 4 * 256) {
+    uint4 xr[4];
 #pragma unroll
-  for (int k = 0; k < GN_PLANES_PER_CTA; ++k) {
-    const int pl = pl0 + k;
-    const __nv_bfloat16* sp = (pl < planes0)
-        ? p.src[0] + ((long long)n * planes0 + pl) * g.PL * 8
-        : p.src[1] + ((long long)n * (p.C[1] >> 3) + (pl - planes0)) * g.PL * 8;
-    in[k] = *reinterpret_cast<const uint4*>(sp + pix);
-  }
-#pragma unroll
-  for (int k = 0; k < GN_PLANES_PER_CTA; ++k) {
-    const int pl = pl0 + k;
-    const int c0 = pl * 8;
-    const uint32_t u[4] = {in[k].x, in[k].y, in[k].z, in[k].w};
-    uint32_t o[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float2 f = unpack_bf16x2(u[e]);
-      float a = f.x * scale[c0 + 2 * e] + shift[c0 + 2 * e];
-      float b = f.y * scale[c0 + 2 * e + 1] + shift[c0 + 2 * e + 1];
-      if (p.silu) { a = silu_f(a); b = silu_f(b); }
-      o[e] = pack_bf16x2(a, b);
+    for (int u = 0; u < 4; ++u) {
+      const int m = m0 + u * 256;
+      xr[u] = (m < mend) ? xv4[m] : make_uint4(0, 0, 0, 0);
     }
-    __nv_bfloat16* dp = p.dst + ((long long)n * (Ct >> 3) + pl) * g.PL * 8;
-    *reinterpret_cast<uint4*>(dp + pix) = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int m = m0 + u * 256;
+      const bool pad = col == p.W;     // the pad column closing every row stays zero
+      col += dcol;
+      if (col >= g.Wp) col -= g.Wp;
+      if (m >= mend) continue;
+      const uint32_t w[4] = {xr[u].x, xr[u].y, xr[u].z, xr[u].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16x2(w[e]);
+        float a = fmaf(f.x, sc[2 * e], sh[2 * e]);
+        float b = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
+        if (p.silu) { a = fmaf(a, tanh_approx(a), a); b = fmaf(b, tanh_approx(b), b); }
+        o[e] = pack_bf16x2(a, b);
+      }
+      dv4[m] = pad ? make_uint4(0, 0, 0, 0) : make_uint4(o[0], o[1], o[2], o[3]);
+    }
   }
 }
 
 cudaError_t launch_gn_apply(const GnApplyParams& p, cudaStream_t s) {
   const int Ct = p.C[0] + p.C[1];
-  dim3 grid((p.H * p.W + 255) / 256, (Ct >> 3) / GN_PLANES_PER_CTA, p.N);
-  const size_t smem = (2 * Ct + 2 * p.groups) * sizeof(float);
-  gn_apply_kernel<<<grid, 256, smem, s>>>(p);
+  if (Ct % p.groups) return cudaErrorInvalidValue;
+  const dim3 grid((p.H * (p.W + 1) + GN_CHUNK - 1) / GN_CHUNK, Ct >> 3, p.N);
+  gn_apply_kernel<<<grid, 256, 0, s>>>(p);
   return cudaGetLastError();
 }
 

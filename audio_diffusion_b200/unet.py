@@ -49,12 +49,16 @@ class _UNetFunction(torch.autograd.Function):
     def forward(ctx, model, x, t, *params):
         out = model._forward_train(x, t)
         ctx.model = model
+        ctx.gen = model._fwd_gen         # the activations live in the model's single workspace: backward must see THIS forward
         ctx.save_for_backward(x)
         return out
 
     @staticmethod
     def backward(ctx, g):
         (x,) = ctx.saved_tensors
+        if ctx.gen != ctx.model._fwd_gen:
+            raise _lib.B200ADError("UNet2DModel(b200): another forward ran on this model before backward(); the saved "
+                                   "activations of this graph were overwritten (one forward per backward)")
         ctx.model._backward_train(x, g)          # fills p.grad (views of the flat gradient buffer)
         return (None, None, None) + (None,) * len(ctx.model._pnames)
 
@@ -171,6 +175,7 @@ class UNet2DModel(nn.Module):
         self._ws = None
         self._ws_key = None
         self._plist = None
+        self._fwd_gen = 0                # bumped by every forward that writes the workspace
 
     # ------------------------------------------------------------------ diffusers ModelMixin persistence
     @classmethod
@@ -266,6 +271,7 @@ class UNet2DModel(nn.Module):
             out = _UNetFunction.apply(self, x, t, *[named[k] for k in self._pnames])
             return UNet2DOutput(out) if return_dict else (out,)
         with torch.cuda.device(x.device):
+            self._fwd_gen += 1
             self._set_training_mode(False)
             self._ensure_bound(n, hh, ww)
             t = self._timesteps(timestep, n, x.device)
@@ -288,6 +294,7 @@ class UNet2DModel(nn.Module):
         L = _lib.lib()
         n, _, hh, ww = x.shape
         with torch.cuda.device(x.device):
+            self._fwd_gen += 1
             self._set_training_mode(True)
             self._ensure_bound(n, hh, ww)
             if getattr(self, "_bwd_key", None) != self._ws_key:
@@ -363,6 +370,7 @@ class UNet2DModel(nn.Module):
         x = self._check_input(sample)
         n, _, hh, ww = x.shape
         with torch.cuda.device(x.device):
+            self._fwd_gen += 1
             self._set_training_mode(False)
             self._ensure_bound(n, hh, ww)
             t = self._timesteps(timestep, n, x.device)

@@ -485,6 +485,33 @@ def run_extras(args, model, dev, rank, world, dist_on):
         ex["c4_vae_decode_s"] = dt
         del lpipe, lunet, vae, zl
         torch.cuda.empty_cache()
+    # ---- batch 1 (the reference facade hard-codes batch_size=1, audiodiffusion/__init__.py:59): device time per step and the
+    # host time it takes to ENQUEUE a step (if the host is faster than the GPU, launch overhead is hidden and a CUDA graph
+    # would not shorten the step)
+    if HW == 256:
+        sch1 = DDPMScheduler()
+        sch1.set_timesteps(DDPM_STEPS)
+        g1 = torch.Generator(device=dev).manual_seed(5)
+        x1 = torch.randn(1, 1, HW, HW, generator=g1, device=dev)
+
+        def step1(i):
+            t = sch1.timesteps[i]
+            z = torch.randn(x1.shape, generator=g1, device=dev)
+            model.forward_step(x1, t, sch1.step_coef(t), noise=z, out=x1)
+        for i in range(5):
+            step1(i)
+        _sync(dist_on)
+        nb1 = 30
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(nb1):
+            step1(5 + i)
+        e1.record()
+        host = time.perf_counter() - t0           # all steps enqueued (no synchronisation yet)
+        torch.cuda.synchronize()
+        ex["b1_step_s"] = e0.elapsed_time(e1) / nb1 * 1e-3
+        ex["b1_host_enqueue_s"] = host / nb1
+        ex["b1_launches"] = float(model.last_launch_count)
     # ---- C5: one train_unet.py iteration (fwd + bwd + all-reduce + clip + AdamW + EMA), batch 16 per GPU
     from audio_diffusion_b200.training import EMAModel, FusedAdamW, train_step
     tb = 16
@@ -537,6 +564,13 @@ def format_extras(ex, world, peak_tf, peak_hbm):
                             "loop_ms_per_step": ex["c4_step_s"] * 1e3, "tail_s": ex["c4_tail_s"],
                             "vae_decode_s_batch128": ex["c4_vae_decode_s"],
                             "loop_tflops": GFLOP_PER_LATENT_FWD * 128 / ex["c4_step_s"] / 1e3}
+    if "b1_step_s" in ex:
+        out["B1_latency"] = {"workload": "audio-diffusion-256 denoise step at batch 1 (the reference facade's batch_size=1 path)",
+                             "ms_per_step": ex["b1_step_s"] * 1e3, "host_enqueue_ms_per_step": ex["b1_host_enqueue_s"] * 1e3,
+                             "gpu_launches_per_step": int(ex["b1_launches"]),
+                             "value": 1.0 / (DDPM_STEPS * ex["b1_step_s"]), "unit": "mel-spectrograms/s",
+                             "tflops": GFLOP_PER_SAMPLE_FWD / ex["b1_step_s"] / 1e3,
+                             "note": "host enqueue time below the device time means launch overhead is hidden behind the GPU"}
     tf = 3 * GFLOP_PER_SAMPLE_FWD * 16 / ex["c5_step_s"] / 1e3
     out["C5_train"] = {"workload": f"train_unet.py iteration 256x256, batch 16 per GPU, dp{world}: fwd + bwd + all-reduce + clip + AdamW + EMA",
                        "value": 16 * world / ex["c5_step_s"], "unit": "images/s", "ms_per_step": ex["c5_step_s"] * 1e3,

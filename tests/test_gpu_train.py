@@ -245,3 +245,20 @@ def test_gradient_accumulation_equals_full_batch(cuda):
     acc = model._grad_flat
     rel = ((acc - full).norm() / full.norm()).item()
     assert rel < 2e-3, rel
+
+
+def test_backward_after_second_forward_is_refused(cuda):
+    """The training forward keeps its activations in the model's single workspace: a second forward before backward()
+    would silently give wrong gradients, so the engine refuses."""
+    from audio_diffusion_b200._lib import B200ADError
+    from audio_diffusion_b200.unet import UNet2DModel
+    model = UNet2DModel(sample_size=(32, 32), seed=3, **TRAIN_CFG).to(cuda).train()
+    x = torch.randn(2, 1, 32, 32, generator=torch.Generator().manual_seed(1)).to(cuda)
+    t = torch.tensor([10, 500]).to(cuda)
+    first = model(x, t)["sample"]
+    with torch.no_grad():
+        model(x, t)                       # e.g. an evaluation call in between
+    with pytest.raises(B200ADError):
+        first.sum().backward()
+    model(x, t)["sample"].sum().backward()      # the latest forward is fine
+    assert all(p.grad is not None for p in model.parameters())
