@@ -26,9 +26,13 @@
 //   overlaps the tail of item i and the head of item i+1 (it was fully exposed, 7 of 34 ms per step, in round 1).
 // Epilogue (8 warps, ~2.7 instructions per element instead of ~7): TMEM -> registers (32x32b: thread = channel, 32
 //   pixels) -> +bias/temb and GroupNorm partial sums on packed fp32 pairs (FADD2/FFMA2) -> cvt.rn.bf16x2 -> four
-//   stmatrix.x4.trans per 32-pixel chunk.  The packed weight rows are interleaved (conv_lane_channel) so that a
-//   transposed 8x8 store lands exactly one PF8 vector (8 channels of one pixel) per 16-byte row -> coalesced 16-byte
-//   global stores, pad columns predicated off.
+//   stmatrix.x4.trans per 32-pixel chunk into one of TWO staging buffers of a 128-pixel tile ([plane][pixel][8 ch] =
+//   finished PF8 runs) -> one bulk store (TMA engine, UBLKCP.G.S) per plane and tile, draining while the next tile is
+//   converted.  The packed weight rows are interleaved (conv_lane_channel) so that a transposed 8x8 store lands exactly
+//   one PF8 vector (8 channels of one pixel) per 16-byte row; pad columns and the run-off behind the image are stored as
+//   the zeros the layout requires there.
+// Small images (H * Wp + bottom halo <= 128 pixels: 8x8 and below): an item's four tiles are the first tiles of four
+//   CONSECUTIVE IMAGES, so one weight fetch and one N = 256 MMA serve several samples (ConvParams::pack).
 // Warp roles (16 warps): 0 activation producer, 1 MMA issuer (uniform datapath, one elected lane), 3 weight producer,
 //   2/8-11 transform (warp 2 also owns the TMEM allocation), 4-7 + 12-15 epilogue.
 #include <cstdlib>
@@ -40,14 +44,10 @@ namespace b200ad {
 constexpr int CONV_THREADS = 512;     // 16 warps
 constexpr int CONV_XF_THREADS = 160;  // transform warps 2, 8, 9, 10, 11
 constexpr int CONV_HALF = 2 * CONV_TM;      // pixels per epilogue half (256 accumulator columns)
-#ifdef CONV_STG_HALF   // round-2 first version: ONE staging buffer of a half item (the second half waits for the first half's store)
-constexpr int CONV_SPLANE = CONV_HALF * 16 + 32;  // epilogue staging: bytes per 8-channel plane (256 pixels x 16 B, +32 B bank skew)
-constexpr int CONV_STAGING = 16 * CONV_SPLANE;    // one half item: 16 planes (128 channels) x 256 pixels, bf16
-#else                  // two buffers of one 128-pixel tile each: the store of tile s drains while tile s+1 is converted
+// epilogue staging: two buffers of one 128-pixel tile each: the store of tile s drains while tile s + 1 is converted
 constexpr int CONV_SPLANE = CONV_TM * 16 + 32;    // bytes per 8-channel plane of a buffer (128 pixels x 16 B, +32 B bank skew)
 constexpr int CONV_STG_BUF = 16 * CONV_SPLANE;    // one tile: 16 planes (128 channels) x 128 pixels, bf16
 constexpr int CONV_STAGING = 2 * CONV_STG_BUF;
-#endif
 
 struct WorkItem {
   int n, ntile, m0, G;
@@ -57,6 +57,12 @@ __device__ __forceinline__ WorkItem decode_work(const ConvParams& p, int w) {
   WorkItem wi;
   wi.ntile = w % p.ntiles_n;
   const int gidx = w / p.ntiles_n;
+  if (p.pack) {   // small images: the item's tiles are the first (only) tiles of p.pack (1, 2 or 4) CONSECUTIVE IMAGES n, n+1, ..
+    wi.n = gidx * p.pack;
+    wi.m0 = 0;
+    wi.G = min(p.pack, p.N - wi.n);
+    return wi;
+  }
   wi.n = gidx / p.groups_per_img;
   const int g = gidx - wi.n * p.groups_per_img;
   wi.m0 = g * (CONV_MAXG * CONV_TM);
@@ -84,7 +90,9 @@ __device__ __forceinline__ uint4 xform_vec(uint4 v, const f32x2_t (&sc)[4], cons
 }
 
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
-  constexpr int AS = CONV_AS, BS = CONV_BS;
+  constexpr int ASM = CONV_AS_MAX, BSM = CONV_BS_MAX;
+  const int AS = p.as;      // activation stages of this launch (CONV_AS .. CONV_AS_MAX)
+  const int BS = p.bs;      // weight-ring depth of this launch (whatever the activation stages leave, CONV_BS .. CONV_BS_MAX)
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -99,13 +107,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bring_base = smem_u32(bring);
   const uint32_t bar_fullA = smem_u32(bars);
-  const uint32_t bar_readyA = smem_u32(bars + AS);
-  const uint32_t bar_emptyA = smem_u32(bars + 2 * AS);
-  const uint32_t bar_fullB = smem_u32(bars + 3 * AS);
-  const uint32_t bar_emptyB = smem_u32(bars + 3 * AS + BS);
-  const uint32_t bar_tfull = smem_u32(bars + 3 * AS + 2 * BS);        // [2]: accumulator half h is complete
-  const uint32_t bar_tempty = smem_u32(bars + 3 * AS + 2 * BS + 2);   // [2]: accumulator half h has been read out
-  static_assert((3 * AS + 2 * BS + 4) * 8 <= 504, "barrier block overflows");
+  const uint32_t bar_readyA = smem_u32(bars + ASM);
+  const uint32_t bar_emptyA = smem_u32(bars + 2 * ASM);
+  const uint32_t bar_fullB = smem_u32(bars + 3 * ASM);
+  const uint32_t bar_emptyB = smem_u32(bars + 3 * ASM + BSM);
+  const uint32_t bar_tfull = smem_u32(bars + 3 * ASM + 2 * BSM);        // [2]: accumulator half h is complete
+  const uint32_t bar_tempty = smem_u32(bars + 3 * ASM + 2 * BSM + 2);   // [2]: accumulator half h has been read out
+  static_assert((3 * ASM + 2 * BSM + 4) * 8 <= 504, "barrier block overflows");
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < AS; ++s) {
@@ -143,20 +151,46 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
         const ConvSeg& sg = p.seg[s];
         const int npix = wi.G * CONV_TM + (sg.ht + sg.hb) * p.Wp + sg.hl + sg.hr;
         const uint32_t row_bytes = (uint32_t)npix * 16u;
-        const int pix0 = p.lead + wi.m0 - sg.ht * p.Wp - sg.hl;
-        const char* src = reinterpret_cast<const char*>(sg.src + (long long)wi.n * sg.img_stride +
-                                                        ((long long)(lane & 1) * p.PL + pix0) * 8);
         const long long src_step = (long long)2 * p.PL * 16;
-        for (int ks = 0; ks < sg.ksteps; ++ks) {
-          const uint32_t full = bar_fullA + 8 * stage;
-          if (lane == 0) {
-            mbar_wait(bar_emptyA + 8 * stage, phase ^ 1);
-            mbar_arrive_expect_tx(full, 2u * row_bytes);
+        if (!p.pack) {
+          const int pix0 = p.lead + wi.m0 - sg.ht * p.Wp - sg.hl;
+          const char* src = reinterpret_cast<const char*>(sg.src + (long long)wi.n * sg.img_stride +
+                                                          ((long long)(lane & 1) * p.PL + pix0) * 8);
+          for (int ks = 0; ks < sg.ksteps; ++ks) {
+            const uint32_t full = bar_fullA + 8 * stage;
+            if (lane == 0) {
+              mbar_wait(bar_emptyA + 8 * stage, phase ^ 1);
+              mbar_arrive_expect_tx(full, 2u * row_bytes);
+            }
+            __syncwarp();
+            if (lane < 2) bulk_g2s(smem_base + stage * a_bytes + (uint32_t)lane * row_bytes, src, row_bytes, full);
+            src += src_step;
+            if (++stage == AS) { stage = 0; phase ^= 1; }
           }
-          __syncwarp();
-          if (lane < 2) bulk_g2s(smem_base + stage * a_bytes + (uint32_t)lane * row_bytes, src, row_bytes, full);
-          src += src_step;
-          if (++stage == AS) { stage = 0; phase ^= 1; }
+        } else {
+          // packed small images: the window is [leading halo | tile 0 = image n | tile 1 = image n+1 | .. | trailing halo];
+          // lane 2g + plane copies tile g (tile 0 with the leading halo, the last tile with the trailing one) of its plane.
+          // Everything behind an image's H * Wp pixels is the zero guard of its own plane.
+          const int g = lane >> 1, lead_px = sg.ht * p.Wp + sg.hl, trail_px = sg.hb * p.Wp + sg.hr;
+          const int cnt = CONV_TM + (g == 0 ? lead_px : 0) + (g == wi.G - 1 ? trail_px : 0);
+          const int doff = (g == 0) ? 0 : lead_px + g * CONV_TM;                      // pixels into the plane's window
+          const int pix0 = p.lead - (g == 0 ? lead_px : 0);
+          const char* src = reinterpret_cast<const char*>(sg.src + (long long)(wi.n + g) * sg.img_stride +
+                                                          ((long long)(lane & 1) * p.PL + pix0) * 8);
+          const bool mine = g < wi.G && lane < 2 * CONV_MAXG;
+          for (int ks = 0; ks < sg.ksteps; ++ks) {
+            const uint32_t full = bar_fullA + 8 * stage;
+            if (lane == 0) {
+              mbar_wait(bar_emptyA + 8 * stage, phase ^ 1);
+              mbar_arrive_expect_tx(full, 2u * row_bytes);
+            }
+            __syncwarp();
+            if (mine)
+              bulk_g2s(smem_base + stage * a_bytes + (uint32_t)(lane & 1) * row_bytes + (uint32_t)doff * 16u, src,
+                       (uint32_t)cnt * 16u, full);
+            src += src_step;
+            if (++stage == AS) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -312,18 +346,40 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++item) {
       const WorkItem wi = decode_work(p, w);
       const int c = wi.ntile * CONV_NT + q * 32 + cw;   // this thread's output channel
-      float bias = p.bias ? __ldg(p.bias + c) : 0.f;
-      if (p.temb) bias += __ldg(p.temb + (long long)wi.n * p.temb_stride + c);
-      const f32x2_t bias2 = f2_pack(bias, bias);
-      // the four 8-channel planes this warp pair writes
-      __nv_bfloat16* out_pl = p.out + (long long)wi.n * out_img_stride + (long long)(wi.ntile * 16 + q * 4) * og.PL * 8;
+      const float bias0 = p.bias ? __ldg(p.bias + c) : 0.f;
+      f32x2_t bias2;
+      __nv_bfloat16* out_pl;     // the four 8-channel planes this warp pair writes
+      // per-sample state (bias + time-embedding row, output image): the item's sample, or - packed small images - tile g's
+      auto set_sample = [&](int n) {
+        float b = bias0;
+        if (p.temb) b += __ldg(p.temb + (long long)n * p.temb_stride + c);
+        bias2 = f2_pack(b, b);
+        out_pl = p.out + (long long)n * out_img_stride + (long long)(wi.ntile * 16 + q * 4) * og.PL * 8;
+      };
+      set_sample(wi.n);
 
       f32x2_t ssum2 = 0ull, ssq2 = 0ull;     // (even pixel, odd pixel) partial sums of this thread's channel
+      // quad (4-channel) partial sums: channels 4k..4k+3 of a plane sit in lanes 4 apart; fp64 atomics into sample n
+      auto flush_stats = [&](int n) {
+        const float2 s2 = f2_unpack(ssum2), q2 = f2_unpack(ssq2);
+        float ssum = s2.x + s2.y, ssq = q2.x + q2.y;
+        ssum += __shfl_xor_sync(0xffffffffu, ssum, 4);
+        ssq += __shfl_xor_sync(0xffffffffu, ssq, 4);
+        ssum += __shfl_xor_sync(0xffffffffu, ssum, 8);
+        ssq += __shfl_xor_sync(0xffffffffu, ssq, 8);
+        if ((lane & 12) == 0) {
+          stat_t* sdst = p.stats + ((long long)n * (p.cout >> 2) + (c >> 2)) * 2;
+          atomicAdd(sdst, (stat_t)ssum);
+          atomicAdd(sdst + 1, (stat_t)ssq);
+        }
+        ssum2 = 0ull;
+        ssq2 = 0ull;
+      };
       const int nchunk = (p.dbg & 8) ? 0 : wi.G * (CONV_TM / 32);
       const uint32_t tsrc = tmem_base + ((uint32_t)(q * 32) << 16);
       // one 32-pixel chunk: +bias, statistics, bf16, transposed store into the staging buffer at pixel offset `spx`
       auto process = [&](const uint32_t (&r)[32], int jc, uint32_t boff, int spx) {
-        const int mc = wi.m0 + jc * 32;
+        const int mc = p.pack ? (jc & 3) * 32 : wi.m0 + jc * 32;   // first pixel of the chunk within its image
         // validity mask of the chunk's 32 pixels: pad columns and the run-off behind the image are written as ZEROS (they
         // are zero guards of the layout) and do not count for the statistics
         uint32_t mask;
@@ -378,53 +434,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
           __syncwarp();
         }
       };
-#ifdef CONV_STG_HALF
-      const int nhalf = (wi.G > 2) ? 2 : 1;
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const bool live = h < nhalf;   // a short item (<= 256 pixels) only uses half 0; half 1 just keeps the barrier phases
-        if (live && !p.up2) {   // the bulk stores of the previous half must have finished READING the staging planes of this quarter
-          if (issuer) bulk_wait_read_all();
-          __syncwarp();
-          named_bar_sync(1 + q, 64);
-        }
-        mbar_wait(bar_tfull + 8 * h, item & 1);   // the MMAs into this half have retired
-        tc_fence_after();
-        const int jbeg = 8 * h, jend = min(nchunk, 8 * h + 8);
-        if (live) {
-          // two register sets: the TMEM load of this warp's next chunk is in flight while the current one is processed;
-          // with the up2 scatter every chunk reuses the warp's own 32-pixel window of the staging planes
-          uint32_t ra[32], rb[32];
-          int jc = jbeg + par;
-          if (jc < jend) { tmem_ld32(tsrc + (uint32_t)(jc * 32), ra); tmem_ld_wait(); }
-          while (jc < jend) {
-            if (jc + 2 < jend) tmem_ld32(tsrc + (uint32_t)((jc + 2) * 32), rb);
-            process(ra, jc, 0u, p.up2 ? par * 32 : (jc - jbeg) * 32);
-            tmem_ld_wait();
-            jc += 2;
-            if (jc >= jend) break;
-            if (jc + 2 < jend) tmem_ld32(tsrc + (uint32_t)((jc + 2) * 32), ra);
-            process(rb, jc, 0u, p.up2 ? par * 32 : (jc - jbeg) * 32);
-            tmem_ld_wait();
-            jc += 2;
-          }
-        }
-        // every TMEM load of this thread from this half has landed: the MMA warp may overwrite it
-        tc_fence_before();
-        mbar_arrive(bar_tempty + 8 * h);
-        if (live && !p.up2) {
-          fence_proxy_async_smem();           // staging rows written through the generic proxy -> visible to the TMA engine
-          named_bar_sync(1 + q, 64);
-          const int npx = min(CONV_HALF, wi.G * CONV_TM - CONV_HALF * h);
-          if (issuer && nchunk > 0 && !(p.dbg & 2)) {
-            bulk_s2g(out_pl + (long long)lane * og.PL * 8 + (long long)(p.lead + wi.m0 + CONV_HALF * h) * 8,
-                     stg_q + (uint32_t)(lane * CONV_SPLANE), (uint32_t)npx * 16u);
-            bulk_commit();
-          }
-        }
-      }
-
-#else
       // The item leaves TMEM tile by tile (128 pixels = 4 chunks; the two warps of a pair take two chunks each) through two
       // staging buffers: while the TMA engine reads tile s out of one buffer, tile s + 1 is converted into the other one.
       // One named barrier per tile: it publishes the tile's staging rows and, because the issuer first waits for its
@@ -438,6 +447,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
         }
         const bool live = sblk < wi.G && nchunk > 0;
         const uint32_t boff = p.up2 ? 0u : (uint32_t)((sblk & 1) * CONV_STG_BUF);
+        if (p.pack && live && sblk > 0) set_sample(wi.n + sblk);   // packed small images: tile g is image n + g
         if (live) {
           uint32_t ra[32], rb[32];
           const int j0 = 4 * sblk + par;
@@ -446,6 +456,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
           tmem_ld_wait();
           process(ra, j0, boff, par * 32);
           process(rb, j0 + 2, boff, p.up2 ? par * 32 : (par + 2) * 32);
+          if (p.pack && do_stats) flush_stats(wi.n + sblk);
         }
         if (sblk & 1) {   // every TMEM load of this thread from this half has landed: the MMA warp may overwrite it
           tc_fence_before();
@@ -457,42 +468,25 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
           __syncwarp();
           named_bar_sync(1 + q, 64);
           if (live && issuer && !(p.dbg & 2)) {
-            bulk_s2g(out_pl + (long long)lane * og.PL * 8 + (long long)(p.lead + wi.m0 + CONV_TM * sblk) * 8,
+            bulk_s2g(out_pl + (long long)lane * og.PL * 8 + (long long)(p.lead + (p.pack ? 0 : wi.m0 + CONV_TM * sblk)) * 8,
                      stg_q + boff + (uint32_t)(lane * CONV_SPLANE), (uint32_t)CONV_TM * 16u);
             bulk_commit();
           }
         }
       }
-#endif
 
-      if (do_stats) {  // quad (4-channel) partial sums: channels 4k..4k+3 of a plane sit in lanes 4 apart; fp64 atomics
-        const float2 s2 = f2_unpack(ssum2), q2 = f2_unpack(ssq2);
-        float ssum = s2.x + s2.y, ssq = q2.x + q2.y;
-        ssum += __shfl_xor_sync(0xffffffffu, ssum, 4);
-        ssq += __shfl_xor_sync(0xffffffffu, ssq, 4);
-        ssum += __shfl_xor_sync(0xffffffffu, ssum, 8);
-        ssq += __shfl_xor_sync(0xffffffffu, ssq, 8);
-        if ((lane & 12) == 0) {
-          stat_t* sdst = p.stats + ((long long)wi.n * (p.cout >> 2) + (c >> 2)) * 2;
-          atomicAdd(sdst, (stat_t)ssum);
-          atomicAdd(sdst + 1, (stat_t)ssq);
-        }
-      }
+      if (do_stats && !p.pack) flush_stats(wi.n);
     }
     if (issuer) bulk_wait_all();   // shared memory must outlive the engine's reads; the stores complete before the CTA exits
   } else {
     // ================================ transform warps (2, 8..11): GroupNorm(+SiLU) of the landed windows, in place.
-    // Every 256-pixel sweep is split into 8 groups of 32 pixels: warps 8, 9, 11 (alone on their sub-partition among the
-    // transform warps) take two groups, warps 2 and 10 (same sub-partition) one each.
-#ifndef CONV_XF_BALANCED   // equal shares (five warps x 1.6 groups does not divide: use 5 of 8 groups per 160-px sweep)
+    // Every 160-pixel sweep of a window is five groups of 32 pixels, one per transform warp.  (Weighting the shares so that
+    // the sub-partition hosting two transform warps, 2 and 10, gets a quarter of the work like the others - 2:2:2:1:1 over a
+    // 256-pixel sweep - measured 2.4 ms / step SLOWER in the in-process A/B of round 2: the longest warp, not the busiest
+    // sub-partition, sets the stage latency.)
     const int xg0 = (warp == 2) ? 0 : (warp - 7);
-    const int xng = 1;
+    constexpr int xng = 1;
     constexpr int XSWEEP = 160;
-#else
-    const int xg0 = (warp == 8) ? 0 : (warp == 9) ? 2 : (warp == 11) ? 4 : (warp == 2) ? 6 : 7;
-    const int xng = (warp == 2 || warp == 10) ? 1 : 2;
-    constexpr int XSWEEP = 256;
-#endif
     int stage = 0;
     uint32_t phase = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
@@ -513,7 +507,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
         const bool silu = sg.silu != 0;
         for (int ks = 0; ks < sg.ksteps; ++ks) {
           f32x2_t sc0[4], sh0[4], sc1[4], sh1[4];
-          if (ssn) {
+          if (ssn && !p.pack) {
             const float4* sp = reinterpret_cast<const float4*>(ssn + ks * 16);
             const float hs = silu ? 0.5f : 1.0f;  // SiLU path works on a/2 (see xform_vec)
 #pragma unroll
@@ -524,7 +518,37 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
             }
           }
           mbar_wait(bar_fullA + 8 * stage, phase);
-          if (ssn && !(p.dbg & 64)) {
+          if (ssn && p.pack && !(p.dbg & 64)) {
+            // packed small images: tile g holds image n + g (its own scale / shift); only the image's valid pixels are
+            // touched - everything else in the window is zero guard from global memory and stays zero
+            uint4* base = reinterpret_cast<uint4*>(smem + stage * a_bytes);
+            const int lead_px = sg.ht * p.Wp + sg.hl, hw = p.H * p.Wp;
+            const int tidx = ((warp == 2) ? 0 : (warp - 7)) * 32 + lane;
+            const float hs = silu ? 0.5f : 1.0f;
+            for (int g = 0; g < wi.G; ++g) {
+              const float4* sp = reinterpret_cast<const float4*>(ssn + (long long)g * sg.ss_stride + ks * 16);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float4 a = __ldg(sp + e), b = __ldg(sp + 4 + e);
+                sc0[e] = f2_pack(a.x * hs, a.z * hs); sh0[e] = f2_pack(a.y * hs, a.w * hs);
+                sc1[e] = f2_pack(b.x * hs, b.z * hs); sh1[e] = f2_pack(b.y * hs, b.w * hs);
+              }
+              for (int m = tidx; m < hw; m += CONV_XF_THREADS) {
+                const int r = m / p.Wp;
+                const int px = lead_px + g * CONV_TM + m;
+                uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);    // pad column: stays zero
+                if (m - r * p.Wp < p.W) {
+                  a = base[px];
+                  b = base[npix + px];
+                  if (silu) { a = xform_vec<true>(a, sc0, sh0); b = xform_vec<true>(b, sc1, sh1); }
+                  else      { a = xform_vec<false>(a, sc0, sh0); b = xform_vec<false>(b, sc1, sh1); }
+                }
+                base[px] = a;
+                base[npix + px] = b;
+              }
+            }
+            fence_proxy_async_smem();
+          } else if (ssn && !(p.dbg & 64)) {
             uint4* base = reinterpret_cast<uint4*>(smem + stage * a_bytes);
             int row[2] = {row0[0], row0[1]}, col[2] = {col0[0], col0[1]};
             for (int px0 = xg0 * 32 + lane; px0 < npix; px0 += XSWEEP) {
@@ -578,24 +602,47 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
       float* gmean = reinterpret_cast<float*>(smem);        // the rings are idle now: [N * groups] mean, then rstd
       float* grstd = gmean + p.N * f.groups;
       const double cnt = (double)cpg * (double)f.HW;
+      // This tail runs on ONE CTA after the grid has drained, so its latency is exposed in every launch (about 15 us before
+      // it was restructured, x 71 GroupNorms per step): the quad sums of a group are fetched as one batch of independent
+      // 16-byte L2 loads (up to 8 in flight per thread) instead of a dependent chain, and the second pass walks (n, c)
+      // incrementally (no integer divisions) with the affine parameters in registers.
       for (int i = threadIdx.x; i < p.N * f.groups; i += CONV_THREADS) {
         const int n = i / f.groups, gi = i - n * f.groups;
         double sm = 0., sq = 0.;
-        for (int c = gi * cpg; c < (gi + 1) * cpg; c += 4) {
-          const stat_t* st = (c < f.C[0]) ? f.stats[0] + ((long long)n * (f.C[0] >> 2) + (c >> 2)) * 2
-                                          : f.stats[1] + ((long long)n * (f.C[1] >> 2) + ((c - f.C[0]) >> 2)) * 2;
-          sm += __ldcg(st);
-          sq += __ldcg(st + 1);
+        for (int c0 = gi * cpg; c0 < (gi + 1) * cpg; c0 += 32) {
+          double2 v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int c = c0 + 4 * k;
+            v[k] = make_double2(0., 0.);
+            if (c < (gi + 1) * cpg) {
+              const stat_t* st = (c < f.C[0]) ? f.stats[0] + ((long long)n * (f.C[0] >> 2) + (c >> 2)) * 2
+                                              : f.stats[1] + ((long long)n * (f.C[1] >> 2) + ((c - f.C[0]) >> 2)) * 2;
+              v[k] = __ldcg(reinterpret_cast<const double2*>(st));
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { sm += v[k].x; sq += v[k].y; }
         }
         const double mean = sm / cnt;
         gmean[i] = (float)mean;
         grstd[i] = (float)(1.0 / sqrt(fmax(sq / cnt - mean * mean, 0.) + (double)f.eps));
       }
       __syncthreads();
-      for (int i = threadIdx.x; i < p.N * Ct; i += CONV_THREADS) {
-        const int n = i / Ct, c = i - n * Ct, gi = n * f.groups + c / cpg;
-        const float sc = __ldg(f.gamma + c) * grstd[gi];
-        f.ss[i] = make_float2(sc, __ldg(f.beta + c) - gmean[gi] * sc);
+      {
+        const int total = p.N * Ct;
+        const int dn = CONV_THREADS / Ct, dc = CONV_THREADS - dn * Ct;
+        const float inv_cpg = 1.0f / (float)cpg;
+        int i = threadIdx.x;
+        int n = i / Ct, c = i - n * Ct;
+        for (; i < total; i += CONV_THREADS) {
+          const int gi = n * f.groups + (int)(((float)c + 0.5f) * inv_cpg);    // c / cpg (exact for these small integers)
+          const float sc = __ldg(f.gamma + c) * grstd[gi];
+          f.ss[i] = make_float2(sc, __ldg(f.beta + c) - gmean[gi] * sc);
+          n += dn;
+          c += dc;
+          if (c >= Ct) { c -= Ct; ++n; }
+        }
       }
       if (threadIdx.x == 0) *f.counter = 0u;
     }
@@ -630,17 +677,60 @@ cudaError_t launch_conv_tc(const ConvParams& p_in, int num_sms, cudaStream_t str
   p.groups_per_img = (p.H * p.Wp + CONV_MAXG * CONV_TM - 1) / (CONV_MAXG * CONV_TM);
   p.ntiles_n = p.cout / CONV_NT;
   p.total_work = p.N * p.groups_per_img * p.ntiles_n;
+  // Small images (8x8 and below at the bottom of the U-Net, every level of the latent model below 16x16): one image is a
+  // fraction of a tile, so an item per image fetches the full weight set (1.2 MB for 512 -> 512) for <= 72 pixels and runs
+  // N = 128 MMAs.  Packed, an item holds the first tile of up to four consecutive images: the window of tile g is image
+  // n + g's plane from its pixel 0 on, whose tail is that image's own zero guard, so every tap of a valid output pixel stays
+  // inside its tile (needs H * Wp + the bottom halo <= 128) and the MMA issue is unchanged.
+  p.pack = 0;
+  if (!(dbg & 256)) {
+    int fits = 1;
+    for (int s = 0; s < p.nseg; ++s) {
+      const ConvSeg& sg = p.seg[s];
+      if (p.H * p.Wp + sg.hb * p.Wp + sg.hr > CONV_TM || sg.ht * p.Wp + sg.hl > CONV_TM) fits = 0;
+    }
+    if (fits) {
+      // images per item: the MMA time of an item grows with its tiles (1 : 2 : 4), the number of waves shrinks with them;
+      // take the fewest (waves x tiles), the larger group on a tie (fewer weight fetches)
+      int best = 1;
+      long long best_cost = -1;
+      for (int g = 1; g <= CONV_MAXG; g *= 2) {
+        const long long items = (long long)((p.N + g - 1) / g) * p.ntiles_n;
+        const long long cost = ((items + num_sms - 1) / num_sms) * g;
+        if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = g; }
+      }
+      p.pack = best;
+      p.total_work = ((p.N + best - 1) / best) * p.ntiles_n;
+    }
+  }
   // the two windows of one k-step must fit an activation slot
   int a_stage = 0;
+  const int tiles_img = (p.H * p.Wp + CONV_TM - 1) / CONV_TM;
+  const int max_g = p.pack ? p.pack : (tiles_img < CONV_MAXG ? tiles_img : CONV_MAXG);   // most tiles any item of this launch has
   for (int s = 0; s < p.nseg; ++s) {
     const ConvSeg& sg = p.seg[s];
-    const int npix = CONV_MAXG * CONV_TM + (sg.ht + sg.hb) * p.Wp + sg.hl + sg.hr;
+    const int npix = max_g * CONV_TM + (sg.ht + sg.hb) * p.Wp + sg.hl + sg.hr;
     a_stage = npix * 32 > a_stage ? npix * 32 : a_stage;
     if (sg.ntaps > CONV_MAXTAPS || sg.ntaps > CONV_BT * (CONV_BS - 1) || npix > 0x3FFF) return cudaErrorInvalidValue;
     for (int t = 0; t < sg.ntaps; ++t) p.seg[s].aoff[t] = (sg.dh[t] + sg.ht) * p.Wp + sg.dw[t] + sg.hl;
   }
   p.a_stage = (a_stage + 255) & ~255;
-  const size_t smem = (size_t)CONV_AS * p.a_stage + (size_t)CONV_BS * CONV_B_SLOT + CONV_STAGING + 1024;
+  // Ring depths: W = 256 fills shared memory with 3 activation stages + 5 weight slots.  Launches with smaller windows (narrow
+  // images, packed small images, 1-tap convs) have SHORT k-steps, and the TMA -> transform -> MMA chain of a stage (a few
+  // thousand cycles of L2 latency) is then covered only by more stages in flight: first up to 6 activation stages, then the
+  // weight ring up to its maximum, then the remaining activation stages.
+  p.as = CONV_AS;
+  p.bs = CONV_BS;
+  if (!(dbg & 512)) {
+    auto fits = [&](int as, int bs) {
+      // 1 KB of head room: the kernel's static shared memory counts against the same 227 KB
+      return (size_t)as * p.a_stage + (size_t)bs * CONV_B_SLOT + CONV_STAGING + 2048 <= (size_t)CONV_SMEM_MAX;
+    };
+    while (p.as < 6 && fits(p.as + 1, p.bs)) ++p.as;
+    while (p.bs < CONV_BS_MAX && fits(p.as, p.bs + 1)) ++p.bs;
+    while (p.as < CONV_AS_MAX && fits(p.as + 1, p.bs)) ++p.as;
+  }
+  const size_t smem = (size_t)p.as * p.a_stage + (size_t)p.bs * CONV_B_SLOT + CONV_STAGING + 1024;
   if (smem > (size_t)CONV_SMEM_MAX) return cudaErrorInvalidValue;  // image too wide for this tiling
   const int grid = p.total_work < num_sms ? p.total_work : num_sms;
   if (grid <= 0) return cudaSuccess;

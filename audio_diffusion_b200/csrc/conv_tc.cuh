@@ -17,8 +17,10 @@ constexpr int CONV_SMEM_MAX = 227 * 1024;
 // grain and the TMA -> transform -> MMA chain of the activations gets a deeper ring.
 constexpr int CONV_BT = 3;                       // taps per weight slot
 constexpr int CONV_B_SLOT = CONV_BT * CONV_B_TAP;
+constexpr int CONV_AS_MAX = 8;    // launches with small windows use more activation stages (see launch_conv_tc)
 constexpr int CONV_AS = 3;   // (4 / 6 measured the same as 3 / 5 in round 1; the bytes now buy the epilogue staging buffer)
-constexpr int CONV_BS = 5;
+constexpr int CONV_BS = 5;        // minimum weight-ring depth (W = 256: shared memory is full)
+constexpr int CONV_BS_MAX = 10;   // launches with smaller activation stages use the rest for a deeper weight ring
 
 // One K-segment: a source tensor (PF8) with its tap set and packed weights. A 3x3 conv is one
 // segment with 9 taps; a fused 1x1 shortcut adds one 1-tap segment per shortcut source; a stride-2
@@ -63,7 +65,10 @@ struct ConvParams {
   int a_stage;          // bytes reserved for the A strips of one stage (set by the launcher)
   int groups_per_img;
   int ntiles_n;         // cout / 128
-  int total_work;       // N * groups_per_img * ntiles_n
+  int total_work;       // N * groups_per_img * ntiles_n  (packed: ceil(N / 4) * ntiles_n)
+  int pack;             // 0, or the images per item (1, 2, 4) for small images (image + bottom halo fit one 128-pixel tile):
+                        // an item's tiles are consecutive images, so a weight fetch and an N = 256 MMA serve several samples
+  int as, bs;           // activation stages / weight-ring slots of this launch (set by the launcher)
   int cout;
   __nv_bfloat16* out;           // PF8, cout channels
   const float* bias;            // [cout]
@@ -74,7 +79,7 @@ struct ConvParams {
   // (2h + oy, 2w + ox) of the (2H, 2W) output tensor. One launch per output parity (oy, ox) with pre-summed 2x2 weights.
   int up2, oy, ox;
   ConvGnFin fin;
-  int dbg;                      // B200AD_CONV_DBG bit flags (timing experiments only): 2 no stores, 4 CTAs out of phase, 8 no epilogue work, 16 no half-by-half boundary k-steps, 32 no weight loads, 64 no transform, 128 reorder 1-tap segments before the last main k-step
+  int dbg;                      // B200AD_CONV_DBG bit flags (timing experiments only): 2 no stores, 4 CTAs out of phase, 8 no epilogue work, 16 no half-by-half boundary k-steps, 32 no weight loads, 64 no transform, 128 reorder 1-tap segments before the last main k-step, 256 no small-image packing, 512 rings fixed at CONV_AS stages / CONV_BS slots
 };
 
 cudaError_t launch_conv_tc(const ConvParams& p, int num_sms, cudaStream_t stream);

@@ -58,6 +58,19 @@ def test_conv3x3_flat(cuda, H, W):
     _conv(cuda, 2, 128, 128, H, W, 3, 1)
 
 
+@pytest.mark.parametrize("N,H,W", [(5, 8, 8), (6, 4, 4), (9, 2, 2), (3, 1, 1), (7, 8, 12)])
+def test_conv3x3_packed_small_images(cuda, N, H, W):
+    """Small images (image + bottom halo inside one 128-pixel tile) are packed up to four per work item: batches that fill
+    items completely and partially, time-embedding bias and residual per SAMPLE, statistics per sample."""
+    _conv(cuda, N, 256, 256, H, W, 3, 1, temb=True, res=True, seed=N)
+    _conv(cuda, N, 128, 128, H, W, 1, 1, seed=N + 1)
+
+
+def test_conv3x3_stride2_to_small_images(cuda):
+    _conv(cuda, 5, 128, 256, 16, 16, 3, 2, seed=9)     # 16x16 -> 8x8: the output (and the parity planes) are packed
+    _conv(cuda, 6, 128, 128, 8, 8, 3, 2, seed=10)
+
+
 def test_conv3x3_wide(cuda):
     _conv(cuda, 2, 128, 128, 8, 128, 3, 1)
     _conv(cuda, 1, 64, 128, 12, 256, 3, 1, seed=3)
@@ -118,7 +131,8 @@ def test_sample_to_u8_bit_exact(cuda):
 
 
 @pytest.mark.parametrize("silu,N,cin,cout,H,W,K", [(1, 2, 128, 128, 32, 32, 3), (0, 1, 256, 128, 16, 16, 1),
-                                                   (1, 1, 128, 256, 8, 128, 3), (1, 2, 384, 128, 16, 16, 3)])
+                                                   (1, 1, 128, 256, 8, 128, 3), (1, 2, 384, 128, 16, 16, 3),
+                                                   (1, 6, 256, 128, 8, 8, 3), (0, 5, 128, 128, 4, 4, 1)])
 def test_fused_groupnorm_conv(cuda, silu, N, cin, cout, H, W, K):
     """conv2d(silu(GroupNorm(x))) with the normalisation applied in the conv kernel's operand staging (transform warps).
     Reference keeps the normalised tensor in fp32; ours rounds it to bf16 before the MMA: tolerance 2.5e-2 * max|ref|."""
@@ -147,7 +161,8 @@ def test_fused_groupnorm_conv(cuda, silu, N, cin, cout, H, W, K):
     assert err <= 2.5e-2 * ref.abs().max().item(), f"err {err} scale {ref.abs().max().item()}"
 
 
-@pytest.mark.parametrize("N,C,cout,H,W", [(2, 128, 128, 16, 16), (1, 128, 256, 8, 64), (1, 256, 128, 4, 128)])
+@pytest.mark.parametrize("N,C,cout,H,W", [(2, 128, 128, 16, 16), (1, 128, 256, 8, 64), (1, 256, 128, 4, 128),
+                                          (5, 128, 128, 8, 8), (6, 256, 128, 4, 4)])
 def test_upsample_conv_folded(cuda, N, C, cout, H, W):
     """conv3x3(nearest_2x(x)) computed as four 2x2 convs with pre-summed weights on the low-res tensor (b200ad_conv2d with
     stride = -2). The weight sums are rounded to bf16 once, so compare against the fp32 reference with 2e-2 * max|ref|."""
@@ -173,7 +188,8 @@ def test_upsample_conv_folded(cuda, N, C, cout, H, W):
     assert (stats.cpu() - s_ref).abs().max().item() <= 3e-2 * s_ref[..., 1].abs().max().item() + 1e-3 * 4 * H * W
 
 
-@pytest.mark.parametrize("N,cin,cout,H,W,K", [(2, 128, 256, 16, 16, 3), (1, 256, 128, 8, 24, 3), (2, 128, 128, 32, 32, 1)])
+@pytest.mark.parametrize("N,cin,cout,H,W,K", [(2, 128, 256, 16, 16, 3), (1, 256, 128, 8, 24, 3), (2, 128, 128, 32, 32, 1),
+                                              (7, 256, 128, 8, 8, 3)])
 def test_conv_dgrad_matches_autograd(cuda, N, cin, cout, H, W, K):
     """b200ad_conv2d_dgrad (forward kernel + transposed / mirrored weight packing) == torch autograd's input gradient of
     F.conv2d(x, w, padding=K//2) for the same upstream gradient (bf16-rounded operands, fp32 reference)."""
