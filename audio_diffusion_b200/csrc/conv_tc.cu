@@ -137,6 +137,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Programmatic dependent launch: this grid may have been started while the previous kernel of the stream was still
+  // draining (its last wave, its last-CTA GroupNorm finalize).  Everything above, and the weight producer's prefetch below,
+  // touches nothing that kernel writes (the packed weights are older); every other role waits for it here.  The next
+  // launch is released at once - it parks at this same point.
+  if (p.pdl) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (warp != 3) asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
+
   if (warp == 0) {
     // ================================ activation producer: per k-step two windows (one per 8-channel plane), lanes 0 / 1
     int stage = 0;
@@ -740,8 +749,24 @@ cudaError_t launch_conv_tc(const ConvParams& p_in, int num_sms, cudaStream_t str
     if (e != cudaSuccess) return e;
     attr = smem;
   }
-  conv_tc_kernel<<<grid, CONV_THREADS, smem, stream>>>(p);
-  return cudaGetLastError();
+  p.pdl = (dbg & 1024) ? 0 : 1;
+  if (!p.pdl) {
+    conv_tc_kernel<<<grid, CONV_THREADS, smem, stream>>>(p);
+    return cudaGetLastError();
+  }
+  // launch with programmatic stream serialization: the grid may begin (prologue, weight prefetch) before its predecessor
+  // has completed; it synchronises on the predecessor itself (griddepcontrol.wait) before touching anything it depends on
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(CONV_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel, p);
 }
 
 // ------------------------------------------------------------------------------------ identity weights

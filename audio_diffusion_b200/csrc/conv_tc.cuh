@@ -69,6 +69,7 @@ struct ConvParams {
   int pack;             // 0, or the images per item (1, 2, 4) for small images (image + bottom halo fit one 128-pixel tile):
                         // an item's tiles are consecutive images, so a weight fetch and an N = 256 MMA serve several samples
   int as, bs;           // activation stages / weight-ring slots of this launch (set by the launcher)
+  int pdl;              // launched with programmatic stream serialization (set by the launcher)
   int cout;
   __nv_bfloat16* out;           // PF8, cout channels
   const float* bias;            // [cout]
@@ -79,7 +80,7 @@ struct ConvParams {
   // (2h + oy, 2w + ox) of the (2H, 2W) output tensor. One launch per output parity (oy, ox) with pre-summed 2x2 weights.
   int up2, oy, ox;
   ConvGnFin fin;
-  int dbg;                      // B200AD_CONV_DBG bit flags (timing experiments only): 2 no stores, 4 CTAs out of phase, 8 no epilogue work, 16 no half-by-half boundary k-steps, 32 no weight loads, 64 no transform, 128 reorder 1-tap segments before the last main k-step, 256 no small-image packing, 512 rings fixed at CONV_AS stages / CONV_BS slots
+  int dbg;                      // B200AD_CONV_DBG bit flags (timing experiments only): 2 no stores, 4 CTAs out of phase, 8 no epilogue work, 16 no half-by-half boundary k-steps, 32 no weight loads, 64 no transform, 128 reorder 1-tap segments before the last main k-step, 256 no small-image packing, 512 rings fixed at CONV_AS stages / CONV_BS slots, 1024 no programmatic dependent launch
 };
 
 cudaError_t launch_conv_tc(const ConvParams& p, int num_sms, cudaStream_t stream);

@@ -36,7 +36,8 @@ struct Act {  // PF8 activation tensor
 enum OpKind { OP_TEMB, OP_CONV_IN, OP_GN, OP_CONV, OP_UPSAMPLE, OP_PARITY, OP_ATTN, OP_CONV_OUT,
               OP_ATTN1 /* single head of dim C */, OP_VAE_SAMPLE, OP_MIX1X1,
               OP_LN /* LayerNorm over channels */, OP_GEGLU, OP_MHA /* multi-head attention, head_dim 16/32/64 */,
-              OP_XVEC /* cross-attention against a one-token encoding = per-sample vector */ };
+              OP_XVEC /* cross-attention against a one-token encoding = per-sample vector */,
+              OP_GNAPPLY /* materialised GroupNorm (attention input: the q/k/v projection has 12 cout tiles) */ };
 struct Op {
   OpKind kind;
   ConvParams conv;
@@ -649,7 +650,21 @@ struct Builder {
 
   Act attention(const std::string& n, const Act& x, bool out_pooled, const std::string& out_tag) {
     const int C = x.C, H = x.H, W = x.W;
-    const float2* ssx = gn_finalize(x, nullptr, n + ".group_norm");
+    // The q/k/v projection is a 1-tap conv with 3C/128 (= 12) cout tiles: fused, every one of those tiles would re-normalise
+    // the same window in its transform warps, and a 1-tap k-step (192 MMA cycles) cannot hide that (measured 187 us per
+    // launch at 16x16, batch 64).  The normalised tensor is tiny here (16 MB): materialise it once, project the plain tensor.
+    Act xn = pooled("attn_xn", C, H, W, false);
+    {
+      Op op{};
+      op.kind = OP_GNAPPLY;
+      GnApplyParams& g = op.gn;
+      g.src[0] = x.p; g.stats[0] = x.stats; g.C[0] = C;
+      g.src[1] = nullptr; g.stats[1] = nullptr; g.C[1] = 0;
+      g.gamma = P(n + ".group_norm.weight"); g.beta = P(n + ".group_norm.bias");
+      g.dst = xn.p;
+      g.N = N; g.H = H; g.W = W; g.groups = h->norm_groups; g.eps = h->norm_eps; g.silu = 0;
+      plan->push_back(op);
+    }
     Act qkv = pooled("qkv", 3 * C, H, W, false);
     {
       Op op{};
@@ -657,8 +672,7 @@ struct Builder {
       ConvParams& p = op.conv;
       conv_common(p, qkv);
       p.nseg = 1;
-      set_seg(p.seg[0], x.p, C, H, W, WP(n + ".qkv#q"), taps_1x1());  // q|k|v blocks are contiguous
-      seg_norm(p.seg[0], ssx, C, false);                               // GroupNorm without SiLU
+      set_seg(p.seg[0], xn.p, C, H, W, WP(n + ".qkv#q"), taps_1x1());  // q|k|v blocks are contiguous
       p.bias = MISC(n + ".bias_qkv");
       p.temb = nullptr; p.temb_stride = 0; p.stats = nullptr;
       plan->push_back(op);

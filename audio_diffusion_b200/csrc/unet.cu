@@ -373,6 +373,10 @@ static int run_plan(b200ad_unet* h, const float* x, const float* t, const float*
         CK(launch_gn_finalize(op.gn, op.ss, st));
         ++launches;
         break;
+      case OP_GNAPPLY:
+        CK(launch_gn_apply(op.gn, st));
+        ++launches;
+        break;
       case OP_CONV:
         CK(launch_conv_tc(op.conv, h->num_sms, st));
         ++launches;

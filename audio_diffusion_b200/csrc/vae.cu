@@ -332,6 +332,7 @@ static int vae_run(b200ad_vae* h, std::vector<Op>& plan, const float* in, const 
         CK(launch_conv_in(op.f0 ? op.f0 : in, op.fw, op.fb, h->N, op.cin, op.H, op.W, op.C, op.dst, op.conv.stats, st));
         break;
       case OP_GN: CK(launch_gn_finalize(op.gn, op.ss, st)); break;
+      case OP_GNAPPLY: CK(launch_gn_apply(op.gn, st)); break;
       case OP_CONV: CK(launch_conv_tc(op.conv, h->num_sms, st)); break;
       case OP_PARITY: CK(launch_parity_split(op.src, op.dst, h->N, op.C, op.H, op.W, st)); break;
       case OP_ATTN1:

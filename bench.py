@@ -319,7 +319,8 @@ def run_b200(args):
     peak_tf, peak_hbm, how = peaks()
     value = B * world / (DDPM_STEPS * ms * 1e-3)
     e2e_call_s = DDPM_STEPS * e2e["step_s"] + e2e["tail_s"]
-    names = {0: "temb", 1: "conv_in", 2: "gn_finalize", 3: "conv_tc", 4: "upsample", 5: "parity_split", 6: "attention", 7: "conv_out"}
+    names = {0: "temb", 1: "conv_in", 2: "gn_finalize", 3: "conv_tc", 4: "upsample", 5: "parity_split", 6: "attention", 7: "conv_out",
+             15: "gn_apply"}
     conv = prof["by_kind"].get(3, [0.0, 0.0, 0])
     step_prof_ms = sum(v[0] for v in prof["by_kind"].values())
     conv_tf = conv[1] / (conv[0] * 1e-3) / 1e12 if conv[0] > 0 else 0.0
@@ -344,7 +345,7 @@ def run_b200(args):
             "kernel_share_of_step": conv[0] / step_prof_ms if step_prof_ms else None,
             "whole_step_tflops": GFLOP_PER_SAMPLE_FWD * B / (ms * 1e-3) / 1e3 if HW == 256 else None,
             "whole_step_frac": (GFLOP_PER_SAMPLE_FWD * B / (ms * 1e-3) / 1e3 / peak_tf) if HW == 256 else None,
-            "ms_by_kernel": {names[k]: round(v[0], 4) for k, v in sorted(prof["by_kind"].items())}}
+            "ms_by_kernel": {names.get(k, f"kind{k}"): round(v[0], 4) for k, v in sorted(prof["by_kind"].items())}}
     cpu = None
     if not args.no_cpu and world == 1:
         cores = _cpu_threads()

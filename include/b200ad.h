@@ -92,7 +92,7 @@ int b200ad_unet_forward_step(b200ad_unet* h, const float* x, const float* t, con
 int b200ad_unet_debug_tensor(b200ad_unet* h, const char* name, float* dst, int* dims, void* stream);
 
 /* Profiling: run one fused step with a CUDA-event pair around every launch of the plan; fills per-op device time
- * (ms), op kind (0 temb, 1 conv_in, 2 gn_finalize, 3 conv_tc, 4 unused, 5 parity_split, 6 attention, 7 conv_out) and, for
+ * (ms), op kind (0 temb, 1 conv_in, 2 gn_finalize, 3 conv_tc, 4 unused, 5 parity_split, 6 attention, 7 conv_out, 15 gn_apply) and, for
  * conv_tc launches, the algorithmic FLOPs (2*N*H*W*cout*K). Synchronises the stream. Returns the number of ops. */
 int b200ad_unet_profile_step(b200ad_unet* h, const float* x, const float* t, const float* z,
                              const b200ad_step_coef* coef, float* x_out, float* op_ms, int* op_kind,
