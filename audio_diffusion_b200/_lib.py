@@ -65,6 +65,8 @@ SYMBOLS = {
     "b200ad_unet_forward": (_I, [_VP, _VP, _VP, _VP, _VP]),
     "b200ad_unet_set_encoding": (_I, [_VP, _VP, _I]),
     "b200ad_unet_forward_step": (_I, [_VP, _VP, _VP, _VP, C.POINTER(StepCoefC), _VP, _VP, _VP]),
+    "b200ad_unet_forward_step_dev": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "b200ad_step_scalars_upload": (_I, [C.POINTER(StepCoefC), C.c_float, _VP, _VP, C.c_int, _VP]),
     "b200ad_unet_profile_step": (_I, [_VP, _VP, _VP, _VP, C.POINTER(StepCoefC), _VP, C.POINTER(C.c_float),
                                       C.POINTER(_I), C.POINTER(C.c_double), _I, _VP]),
     "b200ad_unet_debug_tensor": (_I, [_VP, C.c_char_p, _VP, C.POINTER(_I), _VP]),

@@ -156,26 +156,23 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
     }
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const WorkItem wi = decode_work(p, w);
-      for (int s = 0; s < p.nseg; ++s) {
-        const ConvSeg& sg = p.seg[s];
+      for (int it = 0; it < p.ktotal; ++it) {
+        const int ks = p.sched[it] & 255;
+        const ConvSeg& sg = p.seg[p.sched[it] >> 8];
         const int npix = wi.G * CONV_TM + (sg.ht + sg.hb) * p.Wp + sg.hl + sg.hr;
         const uint32_t row_bytes = (uint32_t)npix * 16u;
-        const long long src_step = (long long)2 * p.PL * 16;
+        const uint32_t full = bar_fullA + 8 * stage;
+        if (lane == 0) {
+          mbar_wait(bar_emptyA + 8 * stage, phase ^ 1);
+          mbar_arrive_expect_tx(full, 2u * row_bytes);
+        }
+        __syncwarp();
+        const long long plane = (long long)(2 * ks + (lane & 1)) * p.PL;     // this lane's 8-channel plane of the k-step
         if (!p.pack) {
           const int pix0 = p.lead + wi.m0 - sg.ht * p.Wp - sg.hl;
-          const char* src = reinterpret_cast<const char*>(sg.src + (long long)wi.n * sg.img_stride +
-                                                          ((long long)(lane & 1) * p.PL + pix0) * 8);
-          for (int ks = 0; ks < sg.ksteps; ++ks) {
-            const uint32_t full = bar_fullA + 8 * stage;
-            if (lane == 0) {
-              mbar_wait(bar_emptyA + 8 * stage, phase ^ 1);
-              mbar_arrive_expect_tx(full, 2u * row_bytes);
-            }
-            __syncwarp();
-            if (lane < 2) bulk_g2s(smem_base + stage * a_bytes + (uint32_t)lane * row_bytes, src, row_bytes, full);
-            src += src_step;
-            if (++stage == AS) { stage = 0; phase ^= 1; }
-          }
+          if (lane < 2)
+            bulk_g2s(smem_base + stage * a_bytes + (uint32_t)lane * row_bytes,
+                     sg.src + (long long)wi.n * sg.img_stride + (plane + pix0) * 8, row_bytes, full);
         } else {
           // packed small images: the window is [leading halo | tile 0 = image n | tile 1 = image n+1 | .. | trailing halo];
           // lane 2g + plane copies tile g (tile 0 with the leading halo, the last tile with the trailing one) of its plane.
@@ -184,23 +181,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
           const int cnt = CONV_TM + (g == 0 ? lead_px : 0) + (g == wi.G - 1 ? trail_px : 0);
           const int doff = (g == 0) ? 0 : lead_px + g * CONV_TM;                      // pixels into the plane's window
           const int pix0 = p.lead - (g == 0 ? lead_px : 0);
-          const char* src = reinterpret_cast<const char*>(sg.src + (long long)(wi.n + g) * sg.img_stride +
-                                                          ((long long)(lane & 1) * p.PL + pix0) * 8);
-          const bool mine = g < wi.G && lane < 2 * CONV_MAXG;
-          for (int ks = 0; ks < sg.ksteps; ++ks) {
-            const uint32_t full = bar_fullA + 8 * stage;
-            if (lane == 0) {
-              mbar_wait(bar_emptyA + 8 * stage, phase ^ 1);
-              mbar_arrive_expect_tx(full, 2u * row_bytes);
-            }
-            __syncwarp();
-            if (mine)
-              bulk_g2s(smem_base + stage * a_bytes + (uint32_t)(lane & 1) * row_bytes + (uint32_t)doff * 16u, src,
-                       (uint32_t)cnt * 16u, full);
-            src += src_step;
-            if (++stage == AS) { stage = 0; phase ^= 1; }
-          }
+          if (g < wi.G && lane < 2 * CONV_MAXG)
+            bulk_g2s(smem_base + stage * a_bytes + (uint32_t)(lane & 1) * row_bytes + (uint32_t)doff * 16u,
+                     sg.src + (long long)(wi.n + g) * sg.img_stride + (plane + pix0) * 8, (uint32_t)cnt * 16u, full);
         }
+        if (++stage == AS) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 3) {
@@ -210,22 +195,22 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
         const int ntile = w % p.ntiles_n;
-        for (int s = 0; s < p.nseg; ++s) {
-          const ConvSeg& sg = p.seg[s];
-          const char* src = reinterpret_cast<const char*>(sg.wpack + (long long)ntile * sg.wtile_stride);
-          for (int ks = 0; ks < sg.ksteps; ++ks) {
-            for (int t0 = 0; t0 < sg.ntaps; t0 += CONV_BT) {
-              const uint32_t bytes = (uint32_t)min(CONV_BT, sg.ntaps - t0) * CONV_B_TAP;
-              mbar_wait(bar_emptyB + 8 * stage, phase ^ 1);
-              if (p.dbg & 32) {      // experiment: no weight traffic at all (bounds what sharing weight fetches could buy)
-                mbar_arrive(bar_fullB + 8 * stage);
-              } else {
-                mbar_arrive_expect_tx(bar_fullB + 8 * stage, bytes);
-                bulk_g2s(bring_base + stage * CONV_B_SLOT, src, bytes, bar_fullB + 8 * stage);
-              }
-              src += bytes;
-              if (++stage == BS) { stage = 0; phase ^= 1; }
+        for (int it = 0; it < p.ktotal; ++it) {
+          const int ks = p.sched[it] & 255;
+          const ConvSeg& sg = p.seg[p.sched[it] >> 8];
+          const char* src = reinterpret_cast<const char*>(sg.wpack + (long long)ntile * sg.wtile_stride +
+                                                          (long long)ks * sg.ntaps * (CONV_B_TAP / 2));
+          for (int t0 = 0; t0 < sg.ntaps; t0 += CONV_BT) {
+            const uint32_t bytes = (uint32_t)min(CONV_BT, sg.ntaps - t0) * CONV_B_TAP;
+            mbar_wait(bar_emptyB + 8 * stage, phase ^ 1);
+            if (p.dbg & 32) {      // experiment: no weight traffic at all (bounds what sharing weight fetches could buy)
+              mbar_arrive(bar_fullB + 8 * stage);
+            } else {
+              mbar_arrive_expect_tx(bar_fullB + 8 * stage, bytes);
+              bulk_g2s(bring_base + stage * CONV_B_SLOT, src, bytes, bar_fullB + 8 * stage);
             }
+            src += bytes;
+            if (++stage == BS) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -253,13 +238,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
         mbar_wait_warp(bar_tempty + 8, epar);
         tc_fence_after();
       }
-      int kidx = 0;
-      for (int s = 0; s < p.nseg; ++s) {
-        const ConvSeg& sg = p.seg[s];
-        const int npix = wi.G * CONV_TM + (sg.ht + sg.hb) * p.Wp + sg.hl + sg.hr;
-        const uint32_t xdesc_lo_hi = ((uint32_t)npix & 0x3FFF) << 16;  // LBO of the pixel windows = npix * 16 B
-        const int ntaps = sg.ntaps;
-        for (int ks = 0; ks < sg.ksteps; ++ks, ++kidx) {
+      for (int kidx = 0; kidx < p.ktotal; ++kidx) {
+        {
+          const ConvSeg& sg = p.seg[p.sched[kidx] >> 8];
+          const int npix = wi.G * CONV_TM + (sg.ht + sg.hb) * p.Wp + sg.hl + sg.hr;
+          const uint32_t xdesc_lo_hi = ((uint32_t)npix & 0x3FFF) << 16;  // LBO of the pixel windows = npix * 16 B
+          const int ntaps = sg.ntaps;
           const bool first = kidx == 0, last = kidx == p.ktotal - 1;
           mbar_wait_warp(bar_readyA + 8 * sa, pa);   // windows landed and (if asked) normalised in place
           const uint32_t abase16 = (smem_base + sa * a_bytes) >> 4;
@@ -500,21 +484,29 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
     uint32_t phase = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const WorkItem wi = decode_work(p, w);
-      for (int s = 0; s < p.nseg; ++s) {
+      int last_s = -1, npix = 0, drow = 0, dcol = 0;
+      const float2* ssn = nullptr;
+      bool silu = false;
+      int row0[2] = {0, 0}, col0[2] = {0, 0};
+      for (int it = 0; it < p.ktotal; ++it) {
+        const int ks = p.sched[it] & 255, s = p.sched[it] >> 8;
         const ConvSeg& sg = p.seg[s];
-        const int npix = wi.G * CONV_TM + (sg.ht + sg.hb) * p.Wp + sg.hl + sg.hr;
-        const float2* ssn = sg.ss ? sg.ss + (long long)wi.n * sg.ss_stride : nullptr;
-        // flat position of this thread's first pixel(s); (row, col) advance incrementally (256 pixels per sweep)
-        int row0[2], col0[2];
+        if (s != last_s) {     // per-segment state (the schedule may alternate between segments)
+          last_s = s;
+          npix = wi.G * CONV_TM + (sg.ht + sg.hb) * p.Wp + sg.hl + sg.hr;
+          ssn = sg.ss ? sg.ss + (long long)wi.n * sg.ss_stride : nullptr;
+          // flat position of this thread's first pixel(s); (row, col) advance incrementally (one sweep per iteration)
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int m_first = wi.m0 - sg.ht * p.Wp - sg.hl + (xg0 + u) * 32 + lane;
-          row0[u] = (m_first >= 0) ? m_first / p.Wp : -1 - ((-1 - m_first) / p.Wp);  // floor division
-          col0[u] = m_first - row0[u] * p.Wp;
+          for (int u = 0; u < 2; ++u) {
+            const int m_first = wi.m0 - sg.ht * p.Wp - sg.hl + (xg0 + u) * 32 + lane;
+            row0[u] = (m_first >= 0) ? m_first / p.Wp : -1 - ((-1 - m_first) / p.Wp);  // floor division
+            col0[u] = m_first - row0[u] * p.Wp;
+          }
+          drow = XSWEEP / p.Wp;
+          dcol = XSWEEP - drow * p.Wp;
+          silu = sg.silu != 0;
         }
-        const int drow = XSWEEP / p.Wp, dcol = XSWEEP - drow * p.Wp;
-        const bool silu = sg.silu != 0;
-        for (int ks = 0; ks < sg.ksteps; ++ks) {
+        {
           f32x2_t sc0[4], sh0[4], sc1[4], sh1[4];
           if (ssn && !p.pack) {
             const float4* sp = reinterpret_cast<const float4*>(ssn + ks * 16);
@@ -682,7 +674,39 @@ cudaError_t launch_conv_tc(const ConvParams& p_in, int num_sms, cudaStream_t str
     p.seg[p.nseg++] = tail;
   }
   p.ktotal = 0;
-  for (int s = 0; s < p.nseg; ++s) p.ktotal += p.seg[s].ksteps;
+  for (int s = 0; s < p.nseg; ++s) {
+    if (p.seg[s].ksteps > 255) return cudaErrorInvalidValue;
+    p.ktotal += p.seg[s].ksteps;
+  }
+  if (p.ktotal > CONV_MAXSCHED) return cudaErrorInvalidValue;
+  {
+    // heavy = many-tap k-steps in segment order, light = 1-tap k-steps in segment order; light ones are spread evenly over
+    // the gaps between heavy ones
+    int nh = 0, nl = 0;
+    for (int s = 0; s < p.nseg; ++s) (p.seg[s].ntaps > 1 ? nh : nl) += p.seg[s].ksteps;
+    int n = 0;
+    // (measured: interleaving is 1.6 ms / step SLOWER than segment-by-segment order - in-process A/B, profiles/ab_conv_r02.txt -
+    //  so it is an experiment switch, B200AD_CONV_DBG & 2048, not the default)
+    if (!(dbg & 2048) || nh < 2 || nl == 0) {
+      for (int s = 0; s < p.nseg; ++s)
+        for (int ks = 0; ks < p.seg[s].ksteps; ++ks) p.sched[n++] = (unsigned short)((s << 8) | ks);
+    } else {
+      int hs = 0, hk = 0, ls = 0, lk = 0;      // cursors (segment, k-step) into the heavy / light sequences
+      auto next = [&](bool heavy, int& cs, int& ck) {
+        while ((p.seg[cs].ntaps > 1) != heavy || ck >= p.seg[cs].ksteps) { ++cs; ck = 0; }
+        p.sched[n++] = (unsigned short)((cs << 8) | ck);
+        ++ck;
+      };
+      int emitted_light = 0;
+      for (int i = 0; i < nh; ++i) {
+        next(true, hs, hk);
+        if (i < nh - 1) {
+          const int want = (int)((long long)(i + 1) * nl / (nh - 1));     // light k-steps due after heavy k-step i
+          for (; emitted_light < want; ++emitted_light) next(false, ls, lk);
+        }
+      }
+    }
+  }
   p.groups_per_img = (p.H * p.Wp + CONV_MAXG * CONV_TM - 1) / (CONV_MAXG * CONV_TM);
   p.ntiles_n = p.cout / CONV_NT;
   p.total_work = p.N * p.groups_per_img * p.ntiles_n;

@@ -9,6 +9,7 @@ constexpr int CONV_TM = 128;        // pixels per tile; an MMA covers up to two 
 constexpr int CONV_MAXG = 4;        // pixel tiles per work item: 4 x 128 fp32 columns = all of TMEM
 constexpr int CONV_MAXSEG = 6;      // K-segments per launch (callers use up to 4; the launcher may split one, see below)
 constexpr int CONV_MAXTAPS = 9;
+constexpr int CONV_MAXSCHED = 256;  // k-steps of one item (all segments); a k-step index within its segment is 8 bits
 constexpr int CONV_B_TAP = 16 * CONV_NT * 2;     // one tap, 16 input channels: 4096 B
 constexpr int CONV_SMEM_MAX = 227 * 1024;
 
@@ -62,6 +63,11 @@ struct ConvParams {
   int nseg;
   int N, H, W, Wp, lead, PL;
   int ktotal;           // sum of the segments' k-steps (set by the launcher)
+  // Order of the k-steps of an item, (segment << 8) | k-step (set by the launcher): segment by segment.  Experiment
+  // (B200AD_CONV_DBG & 2048): many-tap and 1-tap k-steps (shortcut, residual) interleaved - a 1-tap k-step needs a 16 KB
+  // window for 256 MMA cycles (80 B/clk against ~42 B/clk of L2 -> SM throughput), so spreading them between 9-tap k-steps
+  // should hide their loads; measured 1.6 ms / step slower.
+  unsigned short sched[CONV_MAXSCHED];
   int a_stage;          // bytes reserved for the A strips of one stage (set by the launcher)
   int groups_per_img;
   int ntiles_n;         // cout / 128
@@ -80,7 +86,7 @@ struct ConvParams {
   // (2h + oy, 2w + ox) of the (2H, 2W) output tensor. One launch per output parity (oy, ox) with pre-summed 2x2 weights.
   int up2, oy, ox;
   ConvGnFin fin;
-  int dbg;                      // B200AD_CONV_DBG bit flags (timing experiments only): 2 no stores, 4 CTAs out of phase, 8 no epilogue work, 16 no half-by-half boundary k-steps, 32 no weight loads, 64 no transform, 128 reorder 1-tap segments before the last main k-step, 256 no small-image packing, 512 rings fixed at CONV_AS stages / CONV_BS slots, 1024 no programmatic dependent launch
+  int dbg;                      // B200AD_CONV_DBG bit flags (timing experiments only): 2 no stores, 4 CTAs out of phase, 8 no epilogue work, 16 no half-by-half boundary k-steps, 32 no weight loads, 64 no transform, 128 reorder 1-tap segments before the last main k-step, 256 no small-image packing, 512 rings fixed at CONV_AS stages / CONV_BS slots, 1024 no programmatic dependent launch, 2048 interleave 1-tap k-steps between many-tap ones
 };
 
 cudaError_t launch_conv_tc(const ConvParams& p, int num_sms, cudaStream_t stream);

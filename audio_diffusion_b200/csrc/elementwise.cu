@@ -554,11 +554,12 @@ __global__ void __launch_bounds__(256, CO_CTAS_PER_SM) conv_out_kernel(const Con
           const long long idx = (((long long)n * p.cout + co) * p.H + h) * p.W + w;
           if (p.eps_out) p.eps_out[idx] = e;
           if (p.x_out) {
+            const StepCoef cf = p.coef_dev ? *p.coef_dev : p.coef;
             const float xv = p.x[idx];
-            float x0 = (xv - p.coef.sqrt_1m_at * e) * p.coef.inv_sqrt_at;
-            if (p.coef.do_clip) x0 = fminf(fmaxf(x0, -p.coef.clip), p.coef.clip);
-            float rr = p.coef.c_x0 * x0 + p.coef.c_xt * xv + p.coef.c_eps * e;
-            if (p.z) rr += p.coef.c_z * p.z[idx];
+            float x0 = (xv - cf.sqrt_1m_at * e) * cf.inv_sqrt_at;
+            if (cf.do_clip) x0 = fminf(fmaxf(x0, -cf.clip), cf.clip);
+            float rr = cf.c_x0 * x0 + cf.c_xt * xv + cf.c_eps * e;
+            if (p.z) rr += cf.c_z * p.z[idx];
             p.x_out[idx] = rr;
           }
         }

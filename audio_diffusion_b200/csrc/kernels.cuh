@@ -111,6 +111,8 @@ struct ConvOutParams {
   const float* z;             // fp32 NCHW noise or null
   float* x_out;               // fp32 NCHW or null
   StepCoef coef;
+  const StepCoef* coef_dev;   // optional: the coefficients live on the device (CUDA-graph replay: nothing per-step is baked
+                              // into the launch); overrides `coef`
 };
 cudaError_t launch_conv_out(const ConvOutParams& p, cudaStream_t s);
 

@@ -345,7 +345,7 @@ extern "C" int b200ad_unet_bind_workspace(b200ad_unet* h, void* workspace, size_
 }
 
 static int run_plan(b200ad_unet* h, const float* x, const float* t, const float* z, const b200ad_step_coef* coef,
-                    float* x_out, float* eps_out, cudaStream_t st) {
+                    float* x_out, float* eps_out, cudaStream_t st, const b200ad_step_coef* coef_dev = nullptr) {
   if (h->plan.empty()) return set_err("bind_workspace must be called before forward");
   const b200ad_unet_config& c = h->cfg;
   int launches = 0;
@@ -415,6 +415,8 @@ static int run_plan(b200ad_unet* h, const float* x, const float* t, const float*
         ConvOutParams p = op.co;
         p.eps_out = eps_out;
         p.x = x; p.z = z; p.x_out = x_out;
+        static_assert(sizeof(b200ad_step_coef) == sizeof(StepCoef), "step-coefficient layouts differ");
+        p.coef_dev = reinterpret_cast<const StepCoef*>(coef_dev);
         if (coef) {
           p.coef.sqrt_1m_at = coef->sqrt_1m_at; p.coef.inv_sqrt_at = coef->inv_sqrt_at; p.coef.clip = coef->clip;
           p.coef.c_x0 = coef->c_x0; p.coef.c_xt = coef->c_xt; p.coef.c_eps = coef->c_eps; p.coef.c_z = coef->c_z;
@@ -493,6 +495,24 @@ extern "C" int b200ad_unet_forward_step(b200ad_unet* h, const float* x, const fl
                                         const b200ad_step_coef* coef, float* x_out, float* eps_out, void* stream) {
   if (!coef || !x_out) return set_err("coef and x_out are required");
   return run_plan(h, x, t, z, coef, x_out, eps_out, (cudaStream_t)stream);
+}
+// per-step scalars -> device (kernel ARGUMENTS are copied at launch time, so the host may run any number of steps ahead)
+__global__ void step_scalars_kernel(b200ad_step_coef coef, float t, b200ad_step_coef* coef_dev, float* t_dev, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *coef_dev = coef;
+  if (i < n) t_dev[i] = t;
+}
+extern "C" int b200ad_step_scalars_upload(const b200ad_step_coef* coef, float t, b200ad_step_coef* coef_dev, float* t_dev, int n,
+                                          void* stream) {
+  if (!coef || !coef_dev || !t_dev || n < 1) return set_err("step_scalars_upload: bad arguments");
+  step_scalars_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*coef, t, coef_dev, t_dev, n);
+  CK(cudaGetLastError());
+  return 0;
+}
+extern "C" int b200ad_unet_forward_step_dev(b200ad_unet* h, const float* x, const float* t, const float* z,
+                                            const b200ad_step_coef* coef_dev, float* x_out, void* stream) {
+  if (!coef_dev || !x_out) return set_err("coef_dev and x_out are required");
+  return run_plan(h, x, t, z, nullptr, x_out, nullptr, (cudaStream_t)stream, coef_dev);
 }
 extern "C" int b200ad_unet_last_launch_count(const b200ad_unet* h) { return h->last_launches; }
 

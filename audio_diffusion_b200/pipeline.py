@@ -34,6 +34,7 @@ from .unet import UNet2DModel
 from .vae import AutoencoderKL
 
 LATENT_SCALE = 0.18215            # training-time scaling of the VAE latents (:147, :189)
+GRAPH_MAX_BATCH = 8               # batches up to this size run the denoising step as a CUDA-graph replay
 
 # model_index.json entries: [library, class] as upstream diffusers resolves them, so directories written here load in the
 # reference / in diffusers, and directories pushed by the reference's train_unet.py load here.
@@ -210,11 +211,21 @@ class AudioDiffusionPipeline(DiffusionPipeline):
         fused = hasattr(unet, "forward_step") and hasattr(sch, "step_coef")
         extra = {"eta": eta} if isinstance(sch, DDIMScheduler) else {}
         cond = () if encoding is None else (encoding,)
+        # Small batches (the facade's batch_size=1, audiodiffusion/__init__.py:59) are bound by the host enqueueing ~120
+        # launches per step: replay the step as one CUDA graph (same kernels, bit-identical results).
+        stepper = None
+        if (fused and encoding is None and inpaint is None and images.shape[0] <= GRAPH_MAX_BATCH
+                and hasattr(unet, "graph_stepper") and os.environ.get("B200AD_CUDA_GRAPH", "1") != "0"):
+            images = images.to(torch.float32).contiguous()
+            stepper = unet.graph_stepper(images)
         for k, t in enumerate(self.progress_bar(sch.timesteps[start_step:])):
             if fused:
                 z = None
                 if sch.needs_noise(t, eta):           # drawn as scheduler.step would draw it (:171, :178)
                     z = randn_tensor(images.shape, step_generator, images.device, images.dtype)
+                if stepper is not None:
+                    images = stepper.step(t, sch.step_coef(t, eta), z)
+                    continue
                 images = unet.forward_step(images, t, sch.step_coef(t, eta), *cond, noise=z, out=images)
             else:                                     # any model / scheduler pair with the reference's duck type
                 eps = unet(images, t, *cond)["sample"]

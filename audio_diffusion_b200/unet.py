@@ -383,6 +383,10 @@ class UNet2DModel(nn.Module):
                 out.data_ptr(), eps.data_ptr() if eps is not None else None, _lib.stream_ptr()))
         return (out, eps) if want_eps else out
 
+    def graph_stepper(self, sample: torch.Tensor) -> "GraphStepper":
+        """CUDA-graph replay of `forward_step` on `sample` (updated in place): see `GraphStepper`."""
+        return GraphStepper(self, sample)
+
     def debug_tensor(self, name: str) -> torch.Tensor:
         """fp32 NCHW copy of a named internal activation of the last forward (parity tests)."""
         L = _lib.lib()
@@ -396,3 +400,62 @@ class UNet2DModel(nn.Module):
     @property
     def last_launch_count(self) -> int:
         return _lib.lib().b200ad_unet_last_launch_count(self._h)
+
+
+class GraphStepper:
+    """The denoising loop's step as ONE `cudaGraphLaunch`: `x <- scheduler.step(unet(x, t), t, x)` with everything that changes
+    from step to step (timestep, scheduler coefficients, noise) in fixed device buffers (`b200ad_unet_forward_step_dev`).
+
+    Small batches are bound by the host, not by the GPU: at batch 1 and 256x256 the ~120 launches of a step take longer to
+    enqueue than to execute (bench.py `configs.B1_latency`), which is the path the reference facade takes
+    (audiodiffusion/__init__.py:59 hard-codes batch_size=1).  The kernels and their order are those of `forward_step`, so the
+    results are bit-identical to the eager path (tests/test_gpu_pipeline.py::test_graph_stepper_equals_eager)."""
+
+    def __init__(self, model: UNet2DModel, sample: torch.Tensor):
+        if getattr(model, "is_conditional", False):
+            raise NotImplementedError("GraphStepper: unconditional U-Net only")
+        if sample.dtype != torch.float32 or not sample.is_contiguous() or sample.device.type != "cuda":
+            raise ValueError("GraphStepper: the sample must be a contiguous fp32 CUDA tensor (it is updated in place)")
+        self.model, self.x = model, sample
+        n, _, hh, ww = sample.shape
+        dev = sample.device
+        self.t = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.z = torch.zeros_like(sample)
+        self.coef = torch.zeros(32, dtype=torch.uint8, device=dev)          # one b200ad_step_coef
+        L = _lib.lib()
+        with torch.cuda.device(dev), torch.no_grad():
+            model._fwd_gen += 1
+            model._set_training_mode(False)
+            model._ensure_bound(n, hh, ww)
+            scratch = torch.empty_like(sample)
+
+            def enqueue(out):
+                _lib.check(L.b200ad_unet_forward_step_dev(model._h, self.x.data_ptr(), self.t.data_ptr(), self.z.data_ptr(),
+                                                          self.coef.data_ptr(), out.data_ptr(), _lib.stream_ptr()))
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                enqueue(scratch)             # warm-up outside the capture (function attributes, lazy module loading);
+                enqueue(scratch)             # writes to a scratch tensor: the sample is untouched
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                enqueue(self.x)
+            del scratch
+        self._bound = (model._packed_key, model._ws_key)
+
+    def step(self, timestep, coef: StepCoefC, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        m = self.model
+        if (m._packed_key, m._ws_key) != self._bound:
+            raise _lib.B200ADError("GraphStepper: the model was re-bound (weights, batch or mode changed) after the capture")
+        c = StepCoefC(coef.sqrt_1m_at, coef.inv_sqrt_at, coef.clip, coef.c_x0, coef.c_xt, coef.c_eps,
+                      coef.c_z if noise is not None else 0.0, coef.do_clip)
+        with torch.cuda.device(self.x.device):
+            _lib.check(_lib.lib().b200ad_step_scalars_upload(C.byref(c), float(timestep), self.coef.data_ptr(), self.t.data_ptr(),
+                                                             self.t.numel(), _lib.stream_ptr()))
+        if noise is not None:
+            self.z.copy_(noise)
+        m._fwd_gen += 1
+        self.graph.replay()
+        return self.x

@@ -86,6 +86,18 @@ typedef struct {
 int b200ad_unet_forward_step(b200ad_unet* h, const float* x, const float* t, const float* z,
                              const b200ad_step_coef* coef, float* x_out, float* eps_out, void* stream);
 
+/* The same step with the coefficients in DEVICE memory (one b200ad_step_coef): nothing that changes from step to step is a
+ * launch argument (x, t, z, coef_dev, x_out are fixed buffers the caller refreshes), so the launch sequence can be captured
+ * into a CUDA graph once and replayed for every step of the loop (pipeline_audio_diffusion.py:159-185) — the batch-1 path
+ * of the reference facade (audiodiffusion/__init__.py:59) is bound by host launch overhead otherwise.  z must be non-NULL
+ * (steps without noise carry c_z = 0). */
+int b200ad_unet_forward_step_dev(b200ad_unet* h, const float* x, const float* t, const float* z,
+                                 const b200ad_step_coef* coef_dev, float* x_out, void* stream);
+/* Writes one step's scalars to the device buffers the call above reads: *coef_dev = *coef, t_dev[0..n) = t.  The values
+ * travel as kernel arguments, so the host may enqueue many steps ahead of the GPU. */
+int b200ad_step_scalars_upload(const b200ad_step_coef* coef, float t, b200ad_step_coef* coef_dev, float* t_dev, int n,
+                               void* stream);
+
 /* Debug / parity: copy a named internal activation of the last forward to fp32 NCHW.
  * Names follow the oracle taps (e.g. "conv_in", "down_blocks.0.resnets.0", "mid_block.attentions.0").
  * Returns the number of channels, or negative. dst may be NULL to query (dims[0..2] = C, H, W). */

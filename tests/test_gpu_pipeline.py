@@ -240,3 +240,47 @@ def test_golden_reference_driven_images(cuda):
     got = np.stack([np.asarray(im) for im in imgs]).astype(int)
     frac = (np.abs(got - z["images"].astype(int)) <= 2).mean()
     assert frac >= 0.9, frac
+
+
+def test_graph_stepper_equals_eager(cuda):
+    """CUDA-graph replay of the fused step (`UNet2DModel.graph_stepper`, b200ad_unet_forward_step_dev) is the same launch
+    sequence as the eager `forward_step`: bit-identical samples over a few DDPM steps, batch 1 and 2; and the pipeline takes
+    that path for small batches with the same images as with B200AD_CUDA_GRAPH=0."""
+    import os
+    from audio_diffusion_b200.mel import Mel
+    from audio_diffusion_b200.pipeline import AudioDiffusionPipeline
+    from audio_diffusion_b200.schedulers import DDPMScheduler
+    from audio_diffusion_b200.unet import UNet2DModel
+    arch = dict(in_channels=1, out_channels=1, layers_per_block=2, block_out_channels=(128, 256),
+                down_block_types=("DownBlock2D", "AttnDownBlock2D"), up_block_types=("AttnUpBlock2D", "UpBlock2D"))
+    model = UNet2DModel(sample_size=(32, 32), seed=4, **arch).to(cuda)
+    sch = DDPMScheduler()
+    sch.set_timesteps(1000)
+    for n in (1, 2):
+        g = torch.Generator().manual_seed(n)
+        x0 = torch.randn(n, 1, 32, 32, generator=g).to(cuda)
+        zs = [torch.randn(n, 1, 32, 32, generator=g).to(cuda) for _ in range(4)]
+        xe = x0.clone()
+        with torch.no_grad():
+            for i in range(4):
+                t = sch.timesteps[100 + i]
+                xe = model.forward_step(xe, t, sch.step_coef(t), noise=zs[i], out=xe)
+            xg = x0.clone()
+            st = model.graph_stepper(xg)
+            for i in range(4):
+                t = sch.timesteps[100 + i]
+                st.step(t, sch.step_coef(t), zs[i])
+        assert torch.equal(xe, xg), (xe - xg).abs().max().item()
+    pipe = AudioDiffusionPipeline(vqvae=None, unet=model, mel=Mel(x_res=32, y_res=32), scheduler=DDPMScheduler())
+    pipe.set_progress_bar_config(disable=True)
+    outs = []
+    for flag in ("1", "0"):
+        os.environ["B200AD_CUDA_GRAPH"] = flag
+        try:
+            gen = torch.Generator(device=cuda).manual_seed(7)
+            imgs = pipe(batch_size=2, steps=6, generator=gen, return_audio=False)
+        finally:
+            os.environ.pop("B200AD_CUDA_GRAPH", None)
+        outs.append([__import__("numpy").asarray(im) for im in imgs])
+    for a, b in zip(*outs):
+        assert (a == b).all()
