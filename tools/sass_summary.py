@@ -8,7 +8,7 @@ import re
 import subprocess
 import sys
 
-WATCH = ["UTCHMMA", "UTCQMMA", "UTCBAR", "UTCCP", "LDTM", "STTM", "UTCATOM", "UBLKCP", "UTMALDG", "UTMASTG", "UBLKRED",
+WATCH = ["ACQBULK", "PREEXIT", "UTCHMMA", "UTCQMMA", "UTCBAR", "UTCCP", "LDTM", "STTM", "UTCATOM", "UBLKCP", "UTMALDG", "UTMASTG", "UBLKRED",
          "SYNCS", "HMMA", "LDSM", "STSM", "LDGSTS", "FFMA2", "FADD2", "FMUL2", "MUFU.TANH", "MUFU.EX2", "DFMA", "RED", "ATOM", "BAR"]
 
 
