@@ -105,6 +105,7 @@ SYMBOLS = {
     "b200ad_group_norm": (_I, [_VP] * 4 + [_I] * 5 + [C.c_float, _I, _VP, _SZ, _VP]),
     "b200ad_mel_scratch_bytes": (_SZ, [C.POINTER(MelConfigC), _I]),
     "b200ad_mel_encode": (_I, [C.POINTER(MelConfigC), _VP, _VP, _VP, _I, _VP, _SZ, _VP]),
+    "b200ad_mel_encode_ref": (_I, [C.POINTER(MelConfigC), _VP, _VP, _VP, _I, _VP, _VP, _VP, _SZ, _VP]),
     "b200ad_mel_decode": (_I, [C.POINTER(MelConfigC), _VP, _VP, _VP, _I, C.c_uint64, _VP, _SZ, _VP]),
     "b200ad_sample_to_u8": (_I, [_VP, _VP, _SZ, _VP]),
 }

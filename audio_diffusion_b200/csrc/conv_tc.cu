@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < AS; ++s) {
       mbar_init(bar_fullA + 8 * s, 1);
-      mbar_init(bar_readyA + 8 * s, CONV_XF_THREADS);
+      // one arrival per transform WARP (its lanes meet on __syncwarp first); B200AD_CONV_DBG & 4096: one per thread (A/B)
+      mbar_init(bar_readyA + 8 * s, (p.dbg & 4096) ? CONV_XF_THREADS : CONV_XF_THREADS / 32);
       mbar_init(bar_emptyA + 8 * s, 1);
     }
     for (int s = 0; s < BS; ++s) {
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
     }
     for (int h = 0; h < 2; ++h) {
       mbar_init(bar_tfull + 8 * h, 1);
-      mbar_init(bar_tempty + 8 * h, 256);
+      mbar_init(bar_tempty + 8 * h, (p.dbg & 4096) ? 256 : 8);   // one arrival per epilogue warp
     }
     mbar_fence_init();
   }
@@ -453,7 +454,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
         }
         if (sblk & 1) {   // every TMEM load of this thread from this half has landed: the MMA warp may overwrite it
           tc_fence_before();
-          mbar_arrive(bar_tempty + 8 * h);
+          __syncwarp();
+          if (lane == 0 || (p.dbg & 4096)) mbar_arrive(bar_tempty + 8 * h);
         }
         if (!p.up2) {
           if (live) fence_proxy_async_smem();   // staging rows written through the generic proxy -> visible to the TMA engine
@@ -576,7 +578,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_tc_kernel(const __grid_c
             }
             fence_proxy_async_smem();
           }
-          mbar_arrive(bar_readyA + 8 * stage);
+          // every lane has fenced its own writes towards the async proxy; the warp then arrives ONCE (32 same-address
+          // shared-memory atomics per warp and k-step were ~7 % of the kernel's shared-memory wavefronts)
+          __syncwarp();
+          if (lane == 0 || (p.dbg & 4096)) mbar_arrive(bar_readyA + 8 * stage);
           if (++stage == AS) { stage = 0; phase ^= 1; }
         }
       }

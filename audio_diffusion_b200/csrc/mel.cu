@@ -170,19 +170,22 @@ __global__ void __launch_bounds__(256) enc_frame_kernel(const float* __restrict_
   if ((threadIdx.x & 31) == 0) atomicMax(smax + n, __float_as_uint(lmax));
 }
 
-// power_to_db(ref=np.max, amin=1e-10, top_db) followed by mel.py:149 (float32 arithmetic, truncating cast)
-__global__ void enc_db_kernel(const float* __restrict__ mel, const unsigned* __restrict__ smax, uint8_t* __restrict__ img,
-                              int per, float top_db) {
+// power_to_db(ref, amin=1e-10, top_db) followed by mel.py:149 (float32 arithmetic, truncating cast).  ref = np.max(S) (the
+// reference default: `refs` == nullptr) or a caller-supplied value per slice (mel.py:135 accepts any scalar / callable).
+__global__ void enc_db_kernel(const float* __restrict__ mel, const unsigned* __restrict__ smax, const float* __restrict__ refs,
+                              uint8_t* __restrict__ img, int per, float top_db) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y;
   if (i >= per) return;
   const float amin = 1e-10f;
-  const float ref = __uint_as_float(smax[n]);
+  const float vmax = __uint_as_float(smax[n]);
+  const float ref = refs ? fabsf(refs[n]) : vmax;        // librosa: ref_value = np.abs(ref)
+  const float lref = __fmul_rn(10.0f, (float)log10((double)fmaxf(amin, ref)));
   const float s = mel[(size_t)n * per + i];
-  float ls = __fmul_rn(10.0f, (float)log10((double)fmaxf(amin, s)));
-  ls = __fsub_rn(ls, __fmul_rn(10.0f, (float)log10((double)fmaxf(amin, ref))));
-  // log_spec.max() is exactly 0 when ref is the maximum of S
-  ls = fmaxf(ls, __fsub_rn(0.0f, top_db));
+  float ls = __fsub_rn(__fmul_rn(10.0f, (float)log10((double)fmaxf(amin, s))), lref);
+  // log_spec.max() - top_db: exactly -top_db when ref is the maximum of S
+  const float lmax = __fsub_rn(__fmul_rn(10.0f, (float)log10((double)fmaxf(amin, vmax))), lref);
+  ls = fmaxf(ls, __fsub_rn(lmax, top_db));
   float v = __fdiv_rn(__fmul_rn(__fadd_rn(ls, top_db), 255.0f), top_db);
   v = fminf(fmaxf(v, 0.0f), 255.0f);
   img[(size_t)n * per + i] = (uint8_t)(int)__fadd_rn(v, 0.5f);
@@ -391,8 +394,9 @@ static int fft_smem_attr(const void* fn, size_t smem) {
   return 0;
 }
 
-extern "C" int b200ad_mel_encode(const b200ad_mel_config* c, const float* basis_t, const float* audio, uint8_t* images,
-                                 int n, void* scratch, size_t scratch_bytes, void* stream) {
+extern "C" int b200ad_mel_encode_ref(const b200ad_mel_config* c, const float* basis_t, const float* audio, uint8_t* images,
+                                     int n, const float* ref_values, float* mel_power_out, void* scratch,
+                                     size_t scratch_bytes, void* stream) {
   MelDims d;
   if (mel_dims(c, &d)) return -1;
   if (scratch_bytes < b200ad_mel_scratch_bytes(c, n)) return set_err("mel_encode: scratch too small");
@@ -416,9 +420,17 @@ extern "C" int b200ad_mel_encode(const b200ad_mel_config* c, const float* basis_
   enc_frame_kernel<<<dim3(d.T, n), 256, smem, st>>>(audio, basis_t, tw, win, mel, smax, d);
   CK(cudaGetLastError());
   const int per = d.M * d.T;
-  enc_db_kernel<<<dim3((per + 255) / 256, n), 256, 0, st>>>(mel, smax, images, per, (float)c->top_db);
-  CK(cudaGetLastError());
+  if (mel_power_out) CK(cudaMemcpyAsync(mel_power_out, mel, (size_t)n * per * 4, cudaMemcpyDeviceToDevice, st));
+  if (images) {
+    enc_db_kernel<<<dim3((per + 255) / 256, n), 256, 0, st>>>(mel, smax, ref_values, images, per, (float)c->top_db);
+    CK(cudaGetLastError());
+  }
   return 0;
+}
+extern "C" int b200ad_mel_encode(const b200ad_mel_config* c, const float* basis_t, const float* audio, uint8_t* images,
+                                 int n, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!images) return set_err("mel_encode: images is null");
+  return b200ad_mel_encode_ref(c, basis_t, audio, images, n, nullptr, nullptr, scratch, scratch_bytes, stream);
 }
 
 extern "C" int b200ad_mel_decode(const b200ad_mel_config* c, const double* pinv, const uint8_t* images, float* audio, int n,

@@ -124,8 +124,12 @@ class Mel:
         return torch.empty(need, dtype=torch.uint8, device=dev)
 
     # ------------------------------------------------------------------ batched codec (GPU)
-    def audio_slices_to_images(self, slices: Union[np.ndarray, torch.Tensor], device=None) -> torch.Tensor:
-        """(n, slice_size) audio -> (n, y_res, x_res) uint8 on the device (mel.py:145-149, batched)."""
+    def audio_slices_to_images(self, slices: Union[np.ndarray, torch.Tensor], device=None, ref=None) -> torch.Tensor:
+        """(n, slice_size) audio -> (n, y_res, x_res) uint8 on the device (mel.py:145-149, batched).
+        `ref` = None / np.max: `librosa.power_to_db(S, ref=np.max)`, the reference default; a number, or a callable evaluated
+        on every slice's mel power spectrogram S (what power_to_db does with a callable), otherwise."""
+        if ref is not None and ref is not np.max:
+            return self._encode_with_ref(slices, device, ref)
         dev = self._device(device)
         a = torch.as_tensor(np.ascontiguousarray(slices) if isinstance(slices, np.ndarray) else slices)
         a = a.to(device=dev, dtype=torch.float32).contiguous()
@@ -139,6 +143,30 @@ class Mel:
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().b200ad_mel_encode(C.byref(cfg), basis_t.data_ptr(), a.data_ptr(), out.data_ptr(), n,
                                                     scratch.data_ptr(), scratch.numel(), _lib.stream_ptr()))
+        return out
+
+    def _encode_with_ref(self, slices, device, ref) -> torch.Tensor:
+        dev = self._device(device)
+        a = torch.as_tensor(np.ascontiguousarray(slices) if isinstance(slices, np.ndarray) else slices)
+        a = a.to(device=dev, dtype=torch.float32).contiguous()
+        if a.ndim != 2 or a.shape[1] != self.slice_size:
+            raise ValueError(f"expected (n, {self.slice_size}) audio slices, got {tuple(a.shape)}")
+        n = a.shape[0]
+        basis_t, _ = self._constants(dev)
+        out = torch.empty((n, self.y_res, self.x_res), dtype=torch.uint8, device=dev)
+        scratch = self._scratch(n, dev)
+        cfg = self._cfg_c()
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            if callable(ref):      # ref(S) per slice, on the host like librosa (S: float32 (y_res, x_res))
+                power = torch.empty((n, self.y_res, self.x_res), dtype=torch.float32, device=dev)
+                _lib.check(L.b200ad_mel_encode_ref(C.byref(cfg), basis_t.data_ptr(), a.data_ptr(), None, n, None,
+                                                   power.data_ptr(), scratch.data_ptr(), scratch.numel(), _lib.stream_ptr()))
+                refs = torch.tensor([float(ref(p)) for p in power.cpu().numpy()], dtype=torch.float32, device=dev)
+            else:
+                refs = torch.full((n,), float(ref), dtype=torch.float32, device=dev)
+            _lib.check(L.b200ad_mel_encode_ref(C.byref(cfg), basis_t.data_ptr(), a.data_ptr(), out.data_ptr(), n,
+                                               refs.data_ptr(), None, scratch.data_ptr(), scratch.numel(), _lib.stream_ptr()))
         return out
 
     def images_to_audio(self, images: Union[np.ndarray, torch.Tensor], device=None) -> np.ndarray:
@@ -161,12 +189,10 @@ class Mel:
 
     # ------------------------------------------------------------------ reference API (mel.py:135-168)
     def audio_slice_to_image(self, slice: int, ref: Union[float, Callable] = np.max) -> Image.Image:
-        if ref is not np.max:
-            raise NotImplementedError("only ref=np.max (the reference default, the only value it ever passes)")
         y = np.asarray(self.get_audio_slice(slice))
         if len(y) != self.slice_size:
             raise ValueError("slice out of range")
-        img = self.audio_slices_to_images(y[None, :])[0].cpu().numpy()
+        img = self.audio_slices_to_images(y[None, :], ref=ref)[0].cpu().numpy()
         return Image.fromarray(img)
 
     def image_to_audio(self, image: Image.Image) -> np.ndarray:

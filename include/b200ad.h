@@ -225,6 +225,13 @@ size_t b200ad_mel_scratch_bytes(const b200ad_mel_config* cfg, int n);
  * data-independent constant the caller builds once). */
 int b200ad_mel_encode(const b200ad_mel_config* cfg, const float* mel_basis_t, const float* audio, uint8_t* images,
                       int n, void* scratch, size_t scratch_bytes, void* stream);
+/* The same with `ref` of librosa.power_to_db chosen by the caller (mel.py:135 `ref` argument, default np.max):
+ * ref_values (device, float[n], may be NULL = np.max) is the reference power per slice; mel_power_out (device,
+ * float[n][y_res][x_res], may be NULL) receives the mel power spectrogram S a callable `ref(S)` is evaluated on;
+ * images may be NULL when only S is wanted. */
+int b200ad_mel_encode_ref(const b200ad_mel_config* cfg, const float* mel_basis_t, const float* audio, uint8_t* images,
+                          int n, const float* ref_values, float* mel_power_out, void* scratch, size_t scratch_bytes,
+                          void* stream);
 /* uint8 images [n][y_res][x_res] -> audio [n][(x_res-1)*hop_length] fp32. mel.py:162-167.
  * mel_pinv: numpy.linalg.pinv(mel basis in fp64), fp64 [n_fft/2+1][y_res] (device constant).
  * phase_seed seeds the Griffin-Lim random phase (the reference leaves it unseeded). */

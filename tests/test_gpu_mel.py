@@ -87,3 +87,20 @@ def test_decode_one_iteration_deterministic_part(cuda):
     top = np.argsort(e_ref)[-20:]
     ratio = e_got[top].sum() / e_ref[top].sum()
     assert 0.2 < ratio < 1.5, ratio
+
+
+@pytest.mark.parametrize("ref", [1.0, 25.0, "median"])
+def test_encode_with_other_ref(cuda, ref):
+    """`Mel.audio_slice_to_image(slice, ref=...)` (mel.py:135) accepts any scalar or callable for librosa.power_to_db's
+    reference power; the default np.max is the fast path, everything else goes through b200ad_mel_encode_ref."""
+    from audio_diffusion_b200.mel import Mel
+    from oracle import mel_oracle as mo
+    mel = Mel(x_res=64, y_res=64, hop_length=1024)
+    y = _audio(mel.slice_size, seed=3, f=330.0)
+    r = np.median if ref == "median" else ref
+    mel.load_audio(raw_audio=y)
+    got = np.asarray(mel.audio_slice_to_image(0, ref=r))
+    S = mo.melspectrogram(y, 22050, 2048, 1024, 64)
+    want = mo.db_to_u8(mo.power_to_db(S, ref=r, top_db=80), 80)
+    diff = np.abs(got.astype(int) - want.astype(int))
+    assert diff.max() <= 1 and (diff == 0).mean() >= 0.995, (diff.max(), (diff == 0).mean())
