@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_reduce_kernel(const GnBw
 __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_apply_kernel(const GnBwdParams p) {
   __shared__ float coef[4][8];
   __shared__ float gAB[2][8];
+  __shared__ float cred[GB_THREADS / 32][8];
   const int Ct = p.C[0] + p.C[1];
   const int n = blockIdx.z, pl = blockIdx.y;
   const int cpg = Ct / p.groups;
@@ -161,6 +162,8 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_apply_kernel(const GnBwd
   int m0 = blockIdx.x * GB_CHUNK + threadIdx.x;
   int col = m0 % g.Wp;
   const int dcol = GB_THREADS % g.Wp;
+  const bool want_cs = p.csum0 && first;
+  float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (; m0 < mend; m0 += 4 * GB_THREADS) {
     uint4 xr[4], gr[4], ar[4], br[4];
 #pragma unroll
@@ -192,6 +195,24 @@ __global__ void __launch_bounds__(GB_THREADS, 2) gn_bwd_apply_kernel(const GnBwd
         o[e] = k.rstd[e] * (k.gam[e] * gy - (gA[e] + xh * gB[e])) + av[e] + bv[e];
       }
       dv4[m] = pad ? make_uint4(0, 0, 0, 0) : pack8(o);
+      if (want_cs && !pad) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cs[e] += o[e];
+      }
+    }
+  }
+  if (want_cs) {   // per-sample channel sums of the gradient just written (uniform per CTA: `first` depends on blockIdx.y)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float a = warp_sum_f(cs[e]);
+      if (lane == 0) cred[warp][e] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      float t = 0.f;
+      for (int w = 0; w < GB_THREADS / 32; ++w) t += cred[w][threadIdx.x];
+      atomicAdd(p.csum0 + (long long)n * p.C[0] + pl * 8 + threadIdx.x, t);
     }
   }
 }

@@ -17,6 +17,8 @@ struct GnBwdParams {
   float* dgamma;                  // [C0 + C1], accumulated
   float* dbeta;
   float* sums;                    // scratch [N][C0 + C1][2]
+  float* csum0;                   // optional [N][C0]: per-sample channel sums of dst[0] are ADDED here (zeroed by the caller):
+                                  // the bias / time-embedding gradients of the layer that produced src[0] (no chan_sum pass)
   int N, H, W, groups;
   float eps;
   int silu;

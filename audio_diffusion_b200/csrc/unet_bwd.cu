@@ -67,6 +67,12 @@ struct BwdBuilder {
   float* cs = nullptr;                        // [N][maxC] channel sums scratch
   float* gsums = nullptr;                     // GroupNorm backward scratch [N][maxC][2]
   float* gproj = nullptr;                     // [N][temb_rows]
+  // per-sample channel sums produced by the GroupNorm-backward apply pass for the gradient tensor it writes (keyed by that
+  // tensor): the producer's bias gradient then is a reduction over N of a [N][C] array instead of a pass over the tensor
+  float* csum_arena = nullptr;
+  size_t csum_floats = 0, csum_used = 0;
+  std::map<const __nv_bfloat16*, float*> csum_of;
+  const float* last_cs = nullptr;             // [N][C] sums of the latest bias_grad (the time-embedding rows are read from it)
 
   Act act_alloc(int C, int H, int W) {
     Act a;
@@ -182,10 +188,19 @@ struct BwdBuilder {
   // per-channel sums of a gradient -> bias gradient(s); returns the [N][C] scratch (valid until the next chan_sum)
   void bias_grad(const View& g, const std::string& bname, const std::string& bname2 = "") {
     BOp op{};
+    auto it = csum_of.find(g.p);
+    if (it != csum_of.end() && g.img_planes * 8 == g.C) {     // whole tensor, sums already made by the pass that wrote it
+      op.kind = BOp::REDUCE_N;
+      op.f0 = it->second; op.o0 = PG(bname); op.o1 = bname2.empty() ? nullptr : PG(bname2); op.C = g.C;
+      last_cs = it->second;
+      bw->ops.push_back(op);
+      return;
+    }
     op.kind = BOp::CHANSUM;
     op.src = g.p; op.o0 = cs; op.C = g.C; op.a = g.img_planes; op.H = g.H; op.W = g.W;
     op.o1 = PG(bname);                                        // bias gradient(s) accumulated by the same kernel
     op.f1 = bname2.empty() ? nullptr : PG(bname2);
+    last_cs = cs;
     bw->ops.push_back(op);
   }
   Act gn_apply(const std::string& tag, const Act& a, const Act* b, const std::string& norm, bool silu) {
@@ -214,6 +229,17 @@ struct BwdBuilder {
     p.addS = addS; p.add0 = add0;
     p.dgamma = PG(norm + ".weight"); p.dbeta = PG(norm + ".bias");
     p.sums = gsums;
+    p.csum0 = nullptr;
+    {
+      static const bool off = [] { const char* e = getenv("B200AD_NO_CSUM_FUSE"); return e && e[0] == '1'; }();   // A/B switch
+      const size_t need = (size_t)N * a.C;
+      if (!off && csum_used + need <= csum_floats) {
+        p.csum0 = csum_arena ? csum_arena + csum_used : nullptr;
+        csum_of[d0.p] = p.csum0;
+        csum_used += need;
+        if (!csum_arena) csum_of[d0.p] = (float*)1;           // size pass: the plan must have the same shape as the real one
+      }
+    }
     p.N = N; p.H = a.H; p.W = a.W; p.groups = h->norm_groups; p.eps = h->norm_eps; p.silu = silu ? 1 : 0;
     bw->ops.push_back(op);
   }
@@ -247,7 +273,7 @@ struct BwdBuilder {
     {
       BOp op{};
       op.kind = BOp::SCATTER;
-      op.f0 = cs; op.o0 = gproj; op.C = co; op.a = h->temb_rows; op.b = h->temb_row_off.at(n);
+      op.f0 = last_cs; op.o0 = gproj; op.C = co; op.a = h->temb_rows; op.b = h->temb_row_off.at(n);
       bw->ops.push_back(op);
     }
     // conv1
@@ -497,6 +523,14 @@ static int build_backward(b200ad_unet* h, Backward* bw, uint8_t* arena, float* g
   B.cs = (float*)B.mem.take((size_t)h->N * 3 * maxC * sizeof(float));
   B.gsums = (float*)B.mem.take((size_t)h->N * 3 * maxC * 2 * sizeof(float));
   B.gproj = (float*)B.mem.take((size_t)h->N * h->temb_rows * sizeof(float));
+  B.csum_floats = (size_t)h->N * 65536;       // all GroupNorm-backward outputs of the reference architecture: 16 K channels
+  B.csum_arena = (float*)B.mem.take(B.csum_floats * sizeof(float));
+  {
+    BOp z{};
+    z.kind = BOp::MEMSET;
+    z.o0 = B.csum_arena; z.n = (long long)(B.csum_floats * sizeof(float));
+    bw->ops.push_back(z);
+  }
   float* g_act = (float*)B.mem.take((size_t)h->N * D * sizeof(float));   // gradient w.r.t. silu(linear_2)
   float* g_h1 = (float*)B.mem.take((size_t)h->N * D * sizeof(float));
   float* h1v = (float*)B.mem.take((size_t)h->N * D * sizeof(float));
