@@ -51,7 +51,20 @@ struct Backward {
   float* grads = nullptr;
   int launches = 0;
   PackBatch pack_batch;              // one launch for all transposed packs
+  // gradient buckets (data-parallel all-reduce overlapped with the rest of the backward pass): bucket k = floats
+  // [bucket_lo[k], bucket_lo[k+1]); its event is recorded right after the last launch that adds into it
+  std::vector<size_t> bucket_lo;
+  std::vector<cudaEvent_t> bucket_ev;
+  std::vector<int> bucket_last_op;   // index into ops (-1: nothing writes it -> recorded before the first op)
 };
+
+static void free_bucket_events(Backward* bw) {
+  for (cudaEvent_t e : bw->bucket_ev) cudaEventDestroy(e);
+  bw->bucket_ev.clear();
+  bw->bucket_lo.clear();
+  bw->bucket_last_op.clear();
+}
+
 
 namespace b200ad {
 
@@ -640,6 +653,7 @@ static int build_backward(b200ad_unet* h, Backward* bw, uint8_t* arena, float* g
 
 namespace b200ad {
 void release_backward(b200ad_unet* h) {
+  if (h->bwd) free_bucket_events(h->bwd);
   delete h->bwd;
   h->bwd = nullptr;
 }
@@ -692,6 +706,7 @@ extern "C" int b200ad_unet_bind_backward(b200ad_unet* h, void* arena, size_t byt
   }
   if (bytes < need) return set_err("backward arena too small: %zu < %zu", bytes, need);
   CK(cudaMemsetAsync(arena, 0, need, (cudaStream_t)stream));
+  free_bucket_events(h->bwd);          // the op list is rebuilt: buckets must be set again
   if (build_backward(h, h->bwd, (uint8_t*)arena, grads, &need)) return -1;
   h->bwd->arena_bytes = need;
   return 0;
@@ -722,6 +737,8 @@ extern "C" int b200ad_unet_backward(b200ad_unet* h, const float* x, const float*
   launches += 1;
   if (prof) CK(cudaEventRecord(ev[1], st));
   size_t opi = 0;
+  for (size_t k = 0; k < bw->bucket_ev.size(); ++k)
+    if (bw->bucket_last_op[k] < 0) CK(cudaEventRecord(bw->bucket_ev[k], st));
   for (BOp& op : bw->ops) {
     switch (op.kind) {
       case BOp::CONV: CK(launch_conv_tc(op.conv, h->num_sms, st)); break;
@@ -753,6 +770,8 @@ extern "C" int b200ad_unet_backward(b200ad_unet* h, const float* x, const float*
     }
     ++launches;
     if (prof) CK(cudaEventRecord(ev[2 + opi], st));
+    for (size_t k = 0; k < bw->bucket_ev.size(); ++k)
+      if (bw->bucket_last_op[k] == (int)opi) CK(cudaEventRecord(bw->bucket_ev[k], st));
     ++opi;
   }
   bw->launches = launches;
@@ -780,3 +799,35 @@ extern "C" int b200ad_unet_backward(b200ad_unet* h, const float* x, const float*
 }
 
 extern "C" int b200ad_unet_backward_launch_count(const b200ad_unet* h) { return h && h->bwd ? h->bwd->launches : 0; }
+
+extern "C" int b200ad_unet_set_grad_buckets(b200ad_unet* h, int n, const size_t* lo) {
+  if (!h || !h->bwd || !h->bwd->grads) return set_err("set_grad_buckets: bind_backward first");
+  Backward* bw = h->bwd;
+  free_bucket_events(bw);
+  if (n <= 0) return 0;
+  if (n > 64 || !lo || lo[0] != 0 || lo[n] != bw->grad_floats) return set_err("set_grad_buckets: bad bucket table");
+  for (int k = 0; k < n; ++k)
+    if (lo[k + 1] <= lo[k]) return set_err("set_grad_buckets: boundaries must ascend");
+  bw->bucket_lo.assign(lo, lo + n + 1);
+  bw->bucket_last_op.assign(n, -1);
+  // every float* an op may ADD parameter gradients through (an over-approximation only delays an event)
+  for (size_t i = 0; i < bw->ops.size(); ++i) {
+    const BOp& op = bw->ops[i];
+    const float* outs[6] = {op.wg.dw, op.gb.dgamma, op.gb.dbeta, op.o0, op.o1, op.f1};
+    for (const float* q : outs) {
+      if (!q || q < bw->grads || q >= bw->grads + bw->grad_floats) continue;
+      const size_t off = (size_t)(q - bw->grads);
+      for (int k = 0; k < n; ++k)
+        if (off >= lo[k] && off < lo[k + 1]) bw->bucket_last_op[k] = (int)i;
+    }
+  }
+  bw->bucket_ev.resize(n);
+  for (int k = 0; k < n; ++k) CK(cudaEventCreateWithFlags(&bw->bucket_ev[k], cudaEventDisableTiming));
+  return 0;
+}
+
+extern "C" int b200ad_unet_grad_bucket_wait(b200ad_unet* h, int k, void* stream) {
+  if (!h || !h->bwd || k < 0 || k >= (int)h->bwd->bucket_ev.size()) return set_err("grad_bucket_wait: no such bucket");
+  CK(cudaStreamWaitEvent((cudaStream_t)stream, h->bwd->bucket_ev[k], 0));
+  return 0;
+}

@@ -310,6 +310,7 @@ class UNet2DModel(nn.Module):
                 _lib.check(L.b200ad_unet_bind_backward(self._h, self._bwd_arena.data_ptr(), self._bwd_arena.numel(),
                                                        self._grad_flat.data_ptr(), _lib.stream_ptr()))
                 self._bwd_key = self._ws_key
+                self._bucket_key = None          # the library dropped its gradient buckets with the old plan
             out = torch.empty((n, self.out_channels, hh, ww), dtype=torch.float32, device=x.device)
             _lib.check(L.b200ad_unet_forward(self._h, x.data_ptr(), t.data_ptr(), out.data_ptr(), _lib.stream_ptr()))
         return out
@@ -328,8 +329,7 @@ class UNet2DModel(nn.Module):
         with torch.cuda.device(x.device):
             _lib.check(L.b200ad_unet_backward(self._h, x.data_ptr(), g.data_ptr(), 1 if accumulate else 0, _lib.stream_ptr()))
         if not getattr(self, "_no_sync", False):
-            from .parallel import allreduce_mean_
-            allreduce_mean_(self._grad_flat)      # data parallel: one collective over the flat gradient buffer
+            self._allreduce_gradients()
         # Parameter gradients are VIEWS of the flat buffer, assigned directly (no 700-tensor clone / accumulate pass).
         if getattr(self, "_grad_views_key", None) != self._grad_flat.data_ptr():
             named = self._named()
@@ -343,6 +343,36 @@ class UNet2DModel(nn.Module):
             if p.grad is not None and p.grad.data_ptr() != gv.data_ptr():
                 raise _lib.B200ADError("UNet2DModel(b200): p.grad must be None or the engine's own gradient view")
             p.grad = gv
+
+    def _allreduce_gradients(self) -> None:
+        """Data parallel (accelerate's DDP, scripts/train_unet.py:181): mean of the flat gradient buffer over the ranks, ONE
+        collective after the backward pass.  B200AD_AR_OVERLAP=1 (NCCL only) reduces it in four buckets whose collectives
+        start as soon as the backward pass has finished writing them (the engine records an event per bucket).  Measured
+        at 2 GPUs (tools/run_n2_train.sh): 53.1 ms per iteration either way - the backward kernels are persistent CTAs
+        that fill every SM (512 threads x 122 registers, 227 KB of shared memory), so NCCL's CTAs only get SMs at kernel
+        boundaries and the time they hold them is taken from the next kernel: the collective is not free to hide."""
+        import os
+        import torch.distributed as dist
+        from .parallel import allreduce_mean_, allreduce_mean_bucketed_, grad_bucket_bounds
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        flat = self._grad_flat
+        if dist.get_backend() != "nccl" or not flat.is_cuda or os.environ.get("B200AD_AR_OVERLAP", "0") != "1":
+            allreduce_mean_(flat)
+            return
+        L = _lib.lib()
+        key = (flat.data_ptr(), self._bwd_key)
+        if getattr(self, "_bucket_key", None) != key:
+            offs = [L.b200ad_unet_grad_offset(self._h, i) for i in range(len(self._pnames))]
+            self._bucket_bounds = grad_bucket_bounds(offs, flat.numel(), nbuckets=4)
+            arr = (C.c_size_t * len(self._bucket_bounds))(*self._bucket_bounds)
+            _lib.check(L.b200ad_unet_set_grad_buckets(self._h, len(self._bucket_bounds) - 1, arr))
+            self._comm_stream = torch.cuda.Stream(device=flat.device)
+            self._bucket_key = key
+            allreduce_mean_(flat)          # the events of THIS backward were not recorded yet: plain collective once
+            return
+        allreduce_mean_bucketed_(flat, self._bucket_bounds,
+                                 lambda k, sp: _lib.check(L.b200ad_unet_grad_bucket_wait(self._h, k, sp)), self._comm_stream)
 
     def no_sync(self):
         """Like `DistributedDataParallel.no_sync()`: backward passes inside the context skip the gradient all-reduce, so
