@@ -127,8 +127,12 @@ def cpu_step_rate(batch: int, hw: int, steps: int, warmup: int):
 
 
 def _cpu_threads():
-    if torch.get_num_threads() == 1 and (os.cpu_count() or 1) > 2:
-        torch.set_num_threads(max(1, os.cpu_count() // 2))  # torchrun forces OMP_NUM_THREADS=1: use the physical cores
+    """Threads of the CPU arm.  The oracle port (torch CPU convolutions) stops scaling early: on the pool's 128-cpu hosts a
+    denoise step at batch 4 takes 4.8 s with 16 or 32 threads, 6.6 s with torch's default 64 and 55 s with 128
+    (profiles/cpu_threads_r02.txt), so the baseline runs on the count that is FASTEST for it, not on the largest."""
+    want = max(1, min(32, os.cpu_count() or 1))
+    if torch.get_num_threads() != want:
+        torch.set_num_threads(want)
     return torch.get_num_threads()
 
 
