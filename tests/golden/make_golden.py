@@ -6,7 +6,9 @@ container.  Run from the repo root:  python tests/golden/make_golden.py
    table of libb200ad's AutoencoderKL (b200ad_vae_param_name / _shape).
  * pipeline_ddpm_small.npz — audiodiffusion/pipeline_audio_diffusion.py::AudioDiffusionPipeline.__call__ (the reference
    file, on the import shim) driving the fp32 CPU oracle U-Net (seeded synthetic weights, oracle/unet_oracle.py) and the
-   product's DDPMScheduler for 6 steps from a given noise tensor with a CPU step generator: the uint8 images it returns.
+   ORACLE's DDPM scheduler (oracle/schedulers_oracle.py - nothing of the product computes a number in this fixture; the
+   product's own scheduler gives bit-identical images, which the generator asserts) for 6 steps from a given noise tensor
+   with a CPU step generator: the uint8 images it returns.
    The GPU pipeline must reproduce them within the stated tolerance (tests/test_gpu_pipeline.py).
 The numerical content is the oracle's (diffusers cannot be imported here); what the fixtures pin is the reference
 files' own logic: key mapping, loop order, noise draws, float->uint8 conversion.
@@ -40,7 +42,8 @@ def vae_key_map():
 
 def pipeline_small():
     from audiodiffusion.pipeline_audio_diffusion import AudioDiffusionPipeline as RefPipe
-    from diffusers import DDPMScheduler
+    from diffusers import DDPMScheduler as ProductDDPM      # the import shim = the product's scheduler (cross-check only)
+    from oracle.schedulers_oracle import OracleDDPM
     from oracle.unet_oracle import UNetConfig, init_weights, unet_forward
 
     class OracleUNet:
@@ -62,12 +65,17 @@ def pipeline_small():
         def image_to_audio(self, image):
             return np.zeros((self.x_res - 1) * self.hop_length, dtype=np.float32)
 
-    pipe = RefPipe(vqvae=None, unet=OracleUNet(), mel=FakeMel(), scheduler=DDPMScheduler())
-    pipe.set_progress_bar_config(disable=True)
     noise = torch.randn(2, 1, 32, 32, generator=torch.Generator().manual_seed(42))
-    images, _ = pipe(batch_size=2, steps=6, noise=noise.clone(), step_generator=torch.Generator().manual_seed(7),
-                     return_dict=False)
-    arr = np.stack([np.asarray(im) for im in images]).astype(np.uint8)
+
+    def run(scheduler):
+        pipe = RefPipe(vqvae=None, unet=OracleUNet(), mel=FakeMel(), scheduler=scheduler)
+        pipe.set_progress_bar_config(disable=True)
+        images, _ = pipe(batch_size=2, steps=6, noise=noise.clone(), step_generator=torch.Generator().manual_seed(7),
+                         return_dict=False)
+        return np.stack([np.asarray(im) for im in images]).astype(np.uint8)
+    arr = run(OracleDDPM())
+    assert np.array_equal(arr, run(ProductDDPM())), "the product's DDPMScheduler disagrees with the oracle's"
+
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "pipeline_ddpm_small.npz"), noise=noise.numpy(), images=arr,
                         steps=6, weight_seed=11, step_seed=7)
     print("pipeline_ddpm_small.npz", arr.shape, arr.mean())
