@@ -414,8 +414,24 @@ class UNet2DModel(nn.Module):
         return (out, eps) if want_eps else out
 
     def graph_stepper(self, sample: torch.Tensor) -> "GraphStepper":
-        """CUDA-graph replay of `forward_step` on `sample` (updated in place): see `GraphStepper`."""
-        return GraphStepper(self, sample)
+        """CUDA-graph replay of `forward_step`: see `GraphStepper`.  The stepper owns its sample buffer (`stepper.x`, initialised
+        from `sample`) and is cached per shape, so repeated pipeline calls re-use one captured graph as long as the model
+        stays bound the same way (weights, batch, mode)."""
+        x = self._check_input(sample)
+        n, _, hh, ww = x.shape
+        cache = self.__dict__.setdefault("_steppers", {})
+        key = (tuple(x.shape), x.device)
+        st = cache.get(key)
+        if st is not None:
+            with torch.cuda.device(x.device):
+                self._set_training_mode(False)
+                self._ensure_bound(n, hh, ww)
+            if st._bound == (self._packed_key, self._ws_key):
+                st.x.copy_(x)
+                return st
+        st = GraphStepper(self, x.clone())
+        cache[key] = st
+        return st
 
     def debug_tensor(self, name: str) -> torch.Tensor:
         """fp32 NCHW copy of a named internal activation of the last forward (parity tests)."""
@@ -445,7 +461,7 @@ class GraphStepper:
         if getattr(model, "is_conditional", False):
             raise NotImplementedError("GraphStepper: unconditional U-Net only")
         if sample.dtype != torch.float32 or not sample.is_contiguous() or sample.device.type != "cuda":
-            raise ValueError("GraphStepper: the sample must be a contiguous fp32 CUDA tensor (it is updated in place)")
+            raise ValueError("GraphStepper: the sample buffer must be a contiguous fp32 CUDA tensor (it is updated in place)")
         self.model, self.x = model, sample
         n, _, hh, ww = sample.shape
         dev = sample.device

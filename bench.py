@@ -523,7 +523,7 @@ def run_extras(args, model, dev, rank, world, dist_on):
         ex["b1_host_enqueue_s"] = host / nb1
         ex["b1_launches"] = float(model.last_launch_count)
         # the same steps as CUDA-graph replays (what AudioDiffusionPipeline does for batches <= 8)
-        stepper = model.graph_stepper(x1)
+        stepper = model.graph_stepper(x1)       # owns its sample buffer (initialised from x1)
 
         def gstep(i):
             t = sch1.timesteps[i]

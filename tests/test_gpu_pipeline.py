@@ -265,12 +265,17 @@ def test_graph_stepper_equals_eager(cuda):
             for i in range(4):
                 t = sch.timesteps[100 + i]
                 xe = model.forward_step(xe, t, sch.step_coef(t), noise=zs[i], out=xe)
-            xg = x0.clone()
-            st = model.graph_stepper(xg)
+            st = model.graph_stepper(x0)
             for i in range(4):
                 t = sch.timesteps[100 + i]
                 st.step(t, sch.step_coef(t), zs[i])
-        assert torch.equal(xe, xg), (xe - xg).abs().max().item()
+            assert torch.equal(xe, st.x), (xe - st.x).abs().max().item()
+            st2 = model.graph_stepper(x0)          # same shape, model still bound the same way: the cached graph, reset to x0
+            assert st2 is st and torch.equal(st2.x, x0)
+            for i in range(4):
+                t = sch.timesteps[100 + i]
+                st2.step(t, sch.step_coef(t), zs[i])
+            assert torch.equal(xe, st2.x)
     pipe = AudioDiffusionPipeline(vqvae=None, unet=model, mel=Mel(x_res=32, y_res=32), scheduler=DDPMScheduler())
     pipe.set_progress_bar_config(disable=True)
     outs = []
