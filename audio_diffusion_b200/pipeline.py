@@ -215,7 +215,8 @@ class AudioDiffusionPipeline(DiffusionPipeline):
         # launches per step: replay the step as one CUDA graph (same kernels, bit-identical results).
         stepper = None
         if (fused and encoding is None and inpaint is None and images.shape[0] <= GRAPH_MAX_BATCH
-                and hasattr(unet, "graph_stepper") and os.environ.get("B200AD_CUDA_GRAPH", "1") != "0"):
+                and hasattr(unet, "graph_stepper") and not getattr(unet, "is_conditional", False)
+                and os.environ.get("B200AD_CUDA_GRAPH", "1") != "0"):
             stepper = unet.graph_stepper(images)
             images = stepper.x                    # the stepper's own buffer, initialised from the start state
         for k, t in enumerate(self.progress_bar(sch.timesteps[start_step:])):
