@@ -378,3 +378,21 @@ def test_grad_bucket_bounds_are_parameter_boundaries():
     assert b[0] == 0 and b[-1] == tot and all(x < y for x, y in zip(b, b[1:]))
     assert all(x in offs for x in b[1:-1])
     assert grad_bucket_bounds([0], 100, nbuckets=4) == [0, 100]          # a single tensor: one bucket
+
+
+def test_bench_extras_formatting():
+    """bench.py's `configs` object (C3 / C4 / B1 / C5 / Mel) is assembled on the host from a flat {name: seconds} dict that
+    travelled through a max-over-ranks all-reduce: every sub-object and the rates derived from it."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    ex = {"c3_step_s": 0.035, "c3_tail_s": 0.07, "c3_call50_s": 1.82, "mel_encode_s": 0.0013, "mel_decode_s": 0.034,
+          "c4_step_s": 0.0081, "c4_tail_s": 0.18, "c4_vae_decode_s": 0.078, "b1_step_s": 0.0046, "b1_host_enqueue_s": 0.0044,
+          "b1_launches": 123.0, "b1_graph_step_s": 0.0044, "c5_step_s": 0.051, "c5_step_nosync_s": 0.050, "c5_launches": 830.0}
+    out = bench.format_extras(ex, 2, 1439.1, 6572.5)
+    assert set(out) == {"C3_ddim50", "C4_latent", "B1_latency", "C5_train", "mel_codec"}
+    assert abs(out["C3_ddim50"]["value"] - 128 / (50 * 0.035 + 0.07)) < 1e-9
+    assert abs(out["C5_train"]["value"] - 32 / 0.051) < 1e-9 and abs(out["C5_train"]["exposed_allreduce_ms"] - 1.0) < 1e-6
+    assert out["B1_latency"]["ms_per_step"] == 4.4 and out["mel_codec"]["decode_frac"] < 1
